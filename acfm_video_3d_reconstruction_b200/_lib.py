@@ -1,0 +1,81 @@
+"""ctypes binding of libacfm_b200.so (C ABI: include/acfm_b200.h).
+
+The CUDA library is the product; there is no CPU or eager-PyTorch fallback.  Importing this
+module without the built library raises, and every call on a non-CUDA tensor raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacfm_b200.so")
+
+_c_int, _c_f, _c_vp, _c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64
+_pi = ctypes.POINTER(ctypes.c_int)
+
+# name -> argtypes; must list every symbol include/acfm_b200.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "acfm_version": [],
+    "acfm_last_error_string": [],
+    "acfm_project_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_f, _c_f, _c_vp, _c_vp],
+    "acfm_project_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp, _c_vp],
+    "acfm_raster_fwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int,
+                        _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
+                             _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "acfm_raster_fwd_launch_info": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or acfm_video_3d_reconstruction_b200/csrc/build.sh). There is no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_char_p if name == "acfm_last_error_string" else ctypes.c_int
+        _lib = l
+    return _lib
+
+
+def check(status, what):
+    """Map an acfm_status to the exception the reference would raise (SURVEY.md §8b Errors)."""
+    if status == 0:
+        return
+    msg = lib().acfm_last_error_string().decode("utf-8", "replace")
+    if status in (1, 2):
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: {msg}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("acfm_video_3d_reconstruction_b200 runs on CUDA tensors only (no CPU fallback); "
+                               f"got a tensor on {t.device}")
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+# count of kernels launched through the C ABI by this process (bench.py reports it)
+launches = 0
+
+
+def count(n=1):
+    global launches
+    launches += n

@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# Builds libacfm_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+       -ccbin /usr/bin/g++ --fmad=true -Xptxas -v)
+SRCS=(api.cu project.cu raster.cu)
+OBJS=()
+mkdir -p _obj
+for s in "${SRCS[@]}"; do
+  o=_obj/${s%.cu}.o
+  if [[ ! -f $o || $s -nt $o || common.cuh -nt $o || ../../include/acfm_b200.h -nt $o ]]; then
+    "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" 2> "_obj/${s%.cu}.ptxas.log" || { cat "_obj/${s%.cu}.ptxas.log" >&2; exit 1; }
+  fi
+  OBJS+=("$o")
+done
+"$NVCC" -shared -o ../libacfm_b200.so "${OBJS[@]}" -ccbin /usr/bin/g++ -lcudart
+echo "built $(cd .. && pwd)/libacfm_b200.so"

@@ -1,0 +1,144 @@
+"""Autograd-level wrappers of the C-ABI kernels (include/acfm_b200.h).
+
+Each function validates its tensors, calls libacfm_b200.so through ctypes on the tensor's device
+and current stream, and (where differentiable) registers the CUDA backward.  Outputs are
+allocated with torch's caching allocator so autograd / DataParallel gather keep working
+(SURVEY.md §8b "Ownership").
+"""
+import math
+
+import torch
+
+from . import _lib
+
+EYE_Z = 2.732  # look_at_view_transform(eye=(0,0,-2.732)): /root/reference/multiframe/nnutils/nmr.py:144
+SIGMA = 1e-4   # BlendParams(sigma=1e-4): nmr.py:153
+BLUR_SOFT = math.log(1.0 / 1e-4 - 1.0) * 1e-4  # RasterizationSettings.blur_radius: nmr.py:157
+K_SOFT = 20    # faces_per_pixel: nmr.py:158
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise ValueError(f"expected a float32 tensor, got {t.dtype}")
+    return t.contiguous()
+
+
+def _faces_arg(faces, N):
+    """faces (N,F,3) or (1,F,3)/(F,3) int64|int32 -> (tensor kept alive, is_i64, batch stride, F)."""
+    if faces.dtype not in (torch.int64, torch.int32):
+        raise ValueError(f"faces must be int64 or int32, got {faces.dtype}")
+    if faces.dim() == 2:
+        faces = faces[None]
+    if faces.dim() != 3 or faces.shape[-1] != 3:
+        raise ValueError(f"faces must have shape (N,F,3), got {tuple(faces.shape)}")
+    F = faces.shape[1]
+    if faces.shape[0] == 1 or (faces.shape[0] == N and faces.stride(0) == 0):
+        f0 = faces[0].contiguous()
+        return f0, int(faces.dtype == torch.int64), 0, F
+    if faces.shape[0] != N:
+        raise ValueError(f"faces batch {faces.shape[0]} does not match {N} renders")
+    return faces.contiguous(), int(faces.dtype == torch.int64), F * 3, F
+
+
+# -------------------------------------------------------------------------------------------------
+# projection
+# -------------------------------------------------------------------------------------------------
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, cams, offset_z, sx, sy, z_add):
+        _lib.require_cuda(verts, cams)
+        verts, cams = _f32c(verts), _f32c(cams)
+        if verts.dim() != 3 or verts.shape[-1] != 3 or cams.dim() != 2 or cams.shape[-1] != 7:
+            raise ValueError(f"expected verts (NB,V,3) and cams (N,7), got {tuple(verts.shape)}, {tuple(cams.shape)}")
+        NB, V, _ = verts.shape
+        N = cams.shape[0]
+        out = torch.empty((N, V, 3), dtype=torch.float32, device=verts.device)
+        with torch.cuda.device(verts.device):
+            st = _lib.lib().acfm_project_fwd(_lib.ptr(verts), _lib.ptr(cams), N, NB, V, offset_z, sx, sy, z_add,
+                                             _lib.ptr(out), _lib.stream_of(verts))
+        _lib.check(st, "acfm_project_fwd")
+        _lib.count()
+        ctx.save_for_backward(verts, cams)
+        ctx.sx, ctx.sy = sx, sy
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        verts, cams = ctx.saved_tensors
+        NB, V, _ = verts.shape
+        N = cams.shape[0]
+        grad_out = _f32c(grad_out)
+        gv = torch.empty_like(verts) if ctx.needs_input_grad[0] else None
+        gc = torch.empty_like(cams) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(verts.device):
+            st = _lib.lib().acfm_project_bwd(_lib.ptr(verts), _lib.ptr(cams), _lib.ptr(grad_out), N, NB, V, ctx.sx,
+                                             ctx.sy, _lib.ptr(gv), _lib.ptr(gc), _lib.stream_of(verts))
+        _lib.check(st, "acfm_project_bwd")
+        _lib.count()
+        return gv, gc, None, None, None, None
+
+
+def project(verts, cams, offset_z=0.0, sx=1.0, sy=1.0, z_add=0.0):
+    """out = (sx*p.x, sy*p.y, p.z + z_add), p = orthographic_proj_withz(verts[n % NB], cams[n], offset_z)."""
+    return _Project.apply(verts, cams, float(offset_z), float(sx), float(sy), float(z_add))
+
+
+# -------------------------------------------------------------------------------------------------
+# rasterization
+# -------------------------------------------------------------------------------------------------
+def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycentric_coords=False,
+              cull_backfaces=False, sigma=0.0, want_bary=False, want_mask=False):
+    """rasterize_meshes on screen-space verts (no autograd).  Returns dict of pix_to_face / zbuf / dists
+    [/ bary / mask]."""
+    _lib.require_cuda(ndc, faces)
+    ndc = _f32c(ndc)
+    N, V, _ = ndc.shape
+    H = W = int(image_size)
+    K = int(faces_per_pixel)
+    fa, i64, fstride, F = _faces_arg(faces, N)
+    dev = ndc.device
+    p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+    zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+    dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+    bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if want_bary else None
+    mask = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_mask else None
+    with torch.cuda.device(dev):
+        st = _lib.lib().acfm_raster_fwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K,
+                                        float(blur_radius), int(clip_barycentric_coords), int(cull_backfaces),
+                                        float(sigma), _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), _lib.ptr(bary),
+                                        _lib.ptr(mask), _lib.stream_of(ndc))
+    _lib.check(st, "acfm_raster_fwd")
+    _lib.count()
+    return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask)
+
+
+class _SoftSilhouette(torch.autograd.Function):
+    """ndc (N,V,3) -> mask (N,H,W), pix_to_face, zbuf, dists; differentiable in ndc through dists."""
+
+    @staticmethod
+    def forward(ctx, ndc, faces, image_size, blur_radius, K, sigma):
+        fr = rasterize(ndc, faces, image_size, blur_radius, K, sigma=sigma, want_mask=True)
+        ctx.save_for_backward(ndc.contiguous(), faces, fr["pix_to_face"], fr["dists"], fr["mask"])
+        ctx.cfg = (int(image_size), int(K), float(sigma))
+        ctx.mark_non_differentiable(fr["pix_to_face"], fr["zbuf"], fr["dists"])
+        return fr["mask"], fr["pix_to_face"], fr["zbuf"], fr["dists"]
+
+    @staticmethod
+    def backward(ctx, grad_mask, _g1, _g2, _g3):
+        ndc, faces, p2f, dists, mask = ctx.saved_tensors
+        S, K, sigma = ctx.cfg
+        N, V, _ = ndc.shape
+        fa, i64, fstride, F = _faces_arg(faces, N)
+        grad_mask = _f32c(grad_mask)
+        g = torch.empty_like(ndc)
+        with torch.cuda.device(ndc.device):
+            st = _lib.lib().acfm_raster_soft_bwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma,
+                                                 _lib.ptr(p2f), _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(grad_mask),
+                                                 _lib.ptr(g), _lib.stream_of(ndc))
+        _lib.check(st, "acfm_raster_soft_bwd")
+        _lib.count(2)  # memset + kernel
+        return g, None, None, None, None, None
+
+
+def soft_silhouette(ndc, faces, image_size, blur_radius=BLUR_SOFT, faces_per_pixel=K_SOFT, sigma=SIGMA):
+    return _SoftSilhouette.apply(ndc, faces, int(image_size), float(blur_radius), int(faces_per_pixel), float(sigma))

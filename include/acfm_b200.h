@@ -1,0 +1,90 @@
+/*
+ * acfm_b200.h — C ABI of libacfm_b200.so: the B200 (sm_100a) render-and-reproject
+ * hot path of ACFM behind the reference's nnutils/nmr.py, geom_utils.py and
+ * loss_utils.py API.  Plain device pointers + sizes + a cudaStream_t (passed as
+ * void*); no torch types.  All pointers are DEVICE pointers valid for the call
+ * unless stated.  Every entry point returns 0 on success, otherwise an
+ * acfm_status code; acfm_last_error_string() describes the last failure on the
+ * calling thread.  The library allocates nothing persistent and is re-entrant
+ * (the reference runs the renderer from one thread per GPU under DataParallel,
+ * /root/reference/multiframe/main.py:184-193).
+ *
+ * Citations are file:line under /root/reference.
+ */
+#ifndef ACFM_B200_H_
+#define ACFM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ACFM_OK = 0,
+  ACFM_ERR_BAD_ARG = 1,     /* null pointer / negative or inconsistent sizes */
+  ACFM_ERR_UNSUPPORTED = 2, /* size outside what the kernels are built for (e.g. K > 64) */
+  ACFM_ERR_CUDA = 3         /* a CUDA runtime call or launch failed */
+} acfm_status;
+
+int acfm_version(void);
+const char* acfm_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Projection.  Replaces geom_utils.orthographic_proj_withz / orthographic_proj / quat_rotate /
+ * hamilton_product (multiframe/nnutils/geom_utils.py:48-153) and the view set-up of
+ * NeuralRenderer.forward (multiframe/nnutils/nmr.py:144-149; monocular/nnutils/nmr.py:193-198).
+ *
+ *   p   = s * (q (0,X) q*)_xyz + (tx, ty, offset_z)          cam = [s,tx,ty,qw,qx,qy,qz]
+ *   out = (sx * p.x, sy * p.y, p.z + z_add)
+ *
+ * verts  (NB,V,3): render n reads verts[n % NB] (NB == N for the reference call sites; NB = B*T
+ *                  avoids materialising pred_v.repeat(G,1,1), multiframe/main.py:609)
+ * cams   (N,7), out (N,V,3).  One rounding per reference torch op, no FMA contraction: bit-identical
+ * to the reference on CPU and GPU.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_project_fwd(const float* verts, const float* cams, int N, int NB, int V, float offset_z,
+                     float sx, float sy, float z_add, float* out, void* stream);
+
+/* grad_out (N,V,3) -> grad_verts (NB,V,3) (summed over the N/NB renders sharing a mesh, overwritten)
+ * and grad_cams (N,7) (overwritten).  Either output may be NULL. */
+int acfm_project_bwd(const float* verts, const float* cams, const float* grad_out, int N, int NB,
+                     int V, float sx, float sy, float* grad_verts, float* grad_cams, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rasterization.  Replaces pytorch3d.renderer.mesh.rasterize_meshes (PyTorch3D 0.3.0, the
+ * reference's third-party dependency) as reached through MeshRasterizer from
+ * NeuralRenderer.forward (multiframe/nnutils/nmr.py:152-171 soft, K=20;  :173-196 hard, K=1,
+ * clip_barycentric_coords) and OF_NeuralRenderer.forward (:224-238), plus SoftSilhouetteShader /
+ * sigmoid_alpha_blend when sigma > 0.
+ *
+ * ndc    (N,V,3)  screen-space vertices (output of acfm_project_fwd)
+ * faces  (N,F,3) or (1,F,3): int64 if faces_i64 else int32; faces_batch_stride = F*3 or 0 (shared)
+ * Outputs, (N,H,W,K) row-major, -1 padded, sorted by (z, face) ascending:
+ *   pix_to_face int64 packed ids n*F+f;  zbuf f32;  dists f32 signed squared NDC distance;
+ *   bary (N,H,W,K,3) f32 or NULL;  mask (N,H,W) f32 or NULL (requires sigma > 0):
+ *   mask = 1 - prod_k (1 - sigmoid(-dists_k / sigma)).
+ * K <= 64.  Arithmetic is strict IEEE fp32 in PyTorch3D's CPU operator order.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
+                    int N, int V, int F, int H, int W, int K, float blur_radius, int clip_bary,
+                    int cull_backfaces, float sigma, int64_t* pix_to_face, float* zbuf, float* dists,
+                    float* bary, float* mask, void* stream);
+
+/* Backward of rasterize_meshes + sigmoid_alpha_blend for the silhouette
+ * (_C.rasterize_meshes_backward with grad only on dists).
+ * grad_mask (N,H,W); grad_ndc (N,V,3) is overwritten (z component = 0). */
+int acfm_raster_soft_bwd(const float* ndc, const void* faces, int faces_i64,
+                         int64_t faces_batch_stride, int N, int V, int F, int H, int W, int K,
+                         float sigma, const int64_t* pix_to_face, const float* dists,
+                         const float* mask, const float* grad_mask, float* grad_ndc, void* stream);
+
+/* Query: dynamic shared memory (bytes) and CTAs the forward rasterizer launches for a shape
+ * (host-only helper used by bench.py for the launch/roofline accounting). */
+int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes,
+                                int* num_ctas, int* threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACFM_B200_H_ */

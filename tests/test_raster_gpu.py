@@ -1,0 +1,171 @@
+"""GPU parity of the rasterizer path (C ABI -> NeuralRenderer / OF_NeuralRenderer mirrors) against the
+CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): pix_to_face bit-exact away from depth ties — here the kernel uses the
+oracle's (z, face) order and strict IEEE arithmetic, so we demand full equality of pix_to_face, zbuf and
+dists; silhouettes within 1e-5 of the unit range (absolute; a pure relative bound is unreachable for
+1-prod(1-p) near 0 in fp32) and per-render sums within 1e-5 relative; gradients within
+1e-3 relative (max-norm)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pt3d_oracle as orc
+from oracle import torch_ref
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_mask_render(X, faces, cam, S, offset_z, faces_dtype=torch.int64, shared=False, K=20):
+    from acfm_video_3d_reconstruction_b200 import NeuralRenderer
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    r = NeuralRenderer(S, offset_z=offset_z)
+    r.faces_per_pixel = K
+    Xc, cc = torch.from_numpy(X).cuda(), torch.from_numpy(cam).cuda()
+    fc = torch.from_numpy(faces).to(faces_dtype).cuda()
+    if shared:
+        fc = fc[:1].expand(X.shape[0], -1, -1)
+    ndc = r.to_ndc(Xc, cc)
+    mask, p2f, zbuf, dists = F_.soft_silhouette(ndc, fc, S, r.blur_radius, K, r.sigma)
+    return dict(ndc=ndc, mask=mask, pix_to_face=p2f, zbuf=zbuf, dists=dists)
+
+
+def _assert_fragments_equal(gpu, ref):
+    p_g, p_r = gpu["pix_to_face"].cpu().numpy(), ref["pix_to_face"]
+    assert p_g.dtype == np.int64
+    neq = (p_g != p_r)
+    assert not neq.any(), f"pix_to_face differs at {neq.sum()} of {neq.size} entries"
+    assert np.array_equal(gpu["zbuf"].cpu().numpy(), ref["zbuf"])
+    assert np.array_equal(gpu["dists"].cpu().numpy(), ref["dists"])
+    if "mask" in ref and gpu.get("mask") is not None:
+        m_g, m_r = gpu["mask"].cpu().numpy(), ref["mask"]
+        assert np.abs(m_g - m_r).max() <= 1e-5
+        s_g, s_r = m_g.reshape(len(m_g), -1).sum(1), m_r.reshape(len(m_r), -1).sum(1)
+        assert np.all(np.abs(s_g - s_r) <= 1e-5 * np.maximum(s_r, 1e-30))
+
+
+def test_golden_small():
+    g = util.golden("raster_small.npz")
+    N = g["X"].shape[0]
+    faces = np.repeat(g["faces"][None], N, 0)
+    out = _gpu_mask_render(g["X"], faces, g["cam"], 64, 5.0)
+    assert np.array_equal(out["ndc"].cpu().numpy(), g["ndc"])
+    ref = dict(pix_to_face=g["pix_to_face"].astype(np.int64), zbuf=g["zbuf"], dists=g["dists"], mask=g["mask"])
+    _assert_fragments_equal(out, ref)
+
+
+@pytest.mark.parametrize("name,S,offset_z,fdt,shared", [
+    ("bird", 256, 5.0, torch.int64, False),   # monocular config (C1/C2 shapes)
+    ("horse", 256, 0.0, torch.int64, True),   # multiframe config, shared topology (stride-0 faces)
+    ("bird", 128, 5.0, torch.int32, False),   # int32 faces (bird_vis.py caller)
+    ("horse", 100, 0.0, torch.int64, False),  # size not a multiple of the tile/region
+])
+def test_soft_silhouette_vs_oracle(name, S, offset_z, fdt, shared):
+    v, f = util.template(name)
+    N = 4
+    X = util.synth_verts(v, N, seed=S)
+    cam = util.synth_cams(N, seed=S + 1)
+    faces = np.repeat(f[None], N, 0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=offset_z)
+    out = _gpu_mask_render(X, faces, cam, S, offset_z, fdt, shared)
+    assert np.array_equal(out["ndc"].cpu().numpy(), ref["ndc"])
+    _assert_fragments_equal(out, ref)
+    cov = (ref["pix_to_face"][..., 0] >= 0).mean()
+    full = (ref["pix_to_face"][..., -1] >= 0).mean()
+    assert cov > 0.03 and full > 0.005, "test must exercise the K-truncation"
+
+
+def test_highres_k50_vs_oracle():
+    """C4 shape: 2562 v / 5120 f, 512^2, K = 50 (one render; the oracle is O(pixels x faces))."""
+    v, f = util.icosphere(4)
+    v = (v * np.array([0.8, 0.48, 0.4], np.float32)).astype(np.float32)
+    X, cam, faces = v[None], util.synth_cams(1, seed=11), f[None]
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=512, offset_z=0.0, K=50)
+    out = _gpu_mask_render(X, faces, cam, 512, 0.0, K=50)
+    _assert_fragments_equal(out, ref)
+
+
+def test_hard_raster_and_of_renderer_vs_oracle():
+    from acfm_video_3d_reconstruction_b200 import OF_NeuralRenderer
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("horse")
+    N = 3
+    X, cam = util.synth_verts(v, N, seed=3), util.synth_cams(N, seed=4)
+    faces = np.repeat(f[None], N, 0)
+    # texture-branch raster: blur 0, K = 1, clipped barycentrics
+    ref = orc.hard_raster(X, faces, cam, img_size=128, offset_z=0.0)
+    fr = F_.rasterize(torch.from_numpy(ref["ndc"]).cuda(), torch.from_numpy(faces).cuda(), 128, 0.0, 1,
+                      clip_barycentric_coords=True, want_bary=True)
+    _assert_fragments_equal(fr, ref)
+    assert np.array_equal(fr["bary"].cpu().numpy(), ref["bary"])
+    # OF_NeuralRenderer: already-projected verts, no y flip
+    proj = orc.project(X, cam, 0.0)
+    ref_of = orc.of_renderer(proj, faces, img_size=128)
+    p2f = OF_NeuralRenderer(128)(torch.from_numpy(proj).cuda(), torch.from_numpy(faces).cuda())
+    assert p2f.shape == (N, 128, 128, 1) and np.array_equal(p2f.cpu().numpy(), ref_of["pix_to_face"])
+
+
+def test_edge_cases():
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.icosphere(1)
+    v = v * 0.5
+    # (a) mesh completely off screen, (b) behind the camera (z < 0), (c) degenerate faces, (d) duplicated depth (ties)
+    off = v + np.array([5.0, 0, 2.0], np.float32)
+    behind = v + np.array([0, 0, -3.0], np.float32)
+    ok = v + np.array([0, 0, 2.0], np.float32)
+    ndc = np.stack([off, behind, ok, ok]).astype(np.float32)
+    faces = np.repeat(f[None], 4, 0).copy()
+    faces[2, :10] = faces[2, :10, :1]            # zero-area faces
+    faces[3, 40:] = faces[3, :40]                # duplicate faces => exact z ties, broken by face id
+    ref = orc.rasterize(ndc, faces, 64, F_.BLUR_SOFT * 10, 6, want_bary=False)
+    ref["mask"] = orc.sigmoid_alpha_blend(ref["dists"], ref["pix_to_face"], F_.SIGMA)
+    fr = F_.rasterize(torch.from_numpy(ndc).cuda(), torch.from_numpy(faces).cuda(), 64, F_.BLUR_SOFT * 10, 6,
+                      sigma=F_.SIGMA, want_mask=True)
+    _assert_fragments_equal(fr, ref)
+    assert (ref["pix_to_face"][:2] == -1).all() and (ref["pix_to_face"][2:, ..., 0] >= 0).any()
+    # (e) empty batch
+    e = F_.rasterize(torch.zeros(0, 12, 3).cuda(), torch.zeros(0, 20, 3, dtype=torch.int64).cuda(), 32, 0.0, 2)
+    assert e["pix_to_face"].shape == (0, 32, 32, 2)
+    # (f) K out of range -> ValueError like the reference's PyTorch3D checks
+    with pytest.raises(ValueError):
+        F_.rasterize(torch.from_numpy(ndc).cuda(), torch.from_numpy(faces).cuda(), 64, 0.0, 65)
+    # (g) cull_backfaces
+    refc = orc.rasterize(ndc[2:], faces[2:], 64, 0.0, 2, cull_backfaces=True, want_bary=False)
+    frc = F_.rasterize(torch.from_numpy(ndc[2:]).cuda(), torch.from_numpy(faces[2:]).cuda(), 64, 0.0, 2, cull_backfaces=True)
+    _assert_fragments_equal(frc, refc)
+
+
+def test_backward_vs_oracle():
+    """grad wrt screen vertices, then end to end through NeuralRenderer to vertices and cameras."""
+    from acfm_video_3d_reconstruction_b200 import NeuralRenderer
+    v, f = util.template("bird")
+    N, S = 3, 128
+    X, cam = util.synth_verts(v, N, seed=21), util.synth_cams(N, seed=22)
+    faces = np.repeat(f[None], N, 0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
+    rng = np.random.default_rng(1)
+    gm = rng.standard_normal((N, S, S)).astype(np.float32)
+    g_ndc_ref = orc.neural_renderer_mask_backward(ref, faces, gm)
+
+    r = NeuralRenderer(S, offset_z=5.0)
+    Xc = torch.from_numpy(X).cuda().requires_grad_(True)
+    cc = torch.from_numpy(cam).cuda().requires_grad_(True)
+    ndc = r.to_ndc(Xc, cc)
+    ndc.retain_grad()
+    mask, p2f = r(Xc, torch.from_numpy(faces).cuda(), cc)  # public API
+    assert np.array_equal(p2f.cpu().numpy(), ref["pix_to_face"])
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    m2, _, _, _ = F_.soft_silhouette(ndc, torch.from_numpy(faces).cuda(), S)
+    (m2 * torch.from_numpy(gm).cuda()).sum().backward()
+    assert util.rel_err(ndc.grad.cpu().numpy(), g_ndc_ref) < 1e-3
+    gX1, gc1 = Xc.grad.clone(), cc.grad.clone()
+    Xc.grad = None; cc.grad = None
+    (mask * torch.from_numpy(gm).cuda()).sum().backward()
+    assert torch.equal(gX1 != 0, Xc.grad != 0)
+    # chain the oracle's d/d ndc through the (pinned) fp64 projection restatement
+    Xd = torch.from_numpy(X).double().requires_grad_(True)
+    cd = torch.from_numpy(cam).double().requires_grad_(True)
+    (torch_ref.to_ndc(Xd, cd, 5.0) * torch.from_numpy(g_ndc_ref).double()).sum().backward()
+    assert util.rel_err(Xc.grad.cpu().numpy(), Xd.grad.numpy()) < 1e-3
+    assert util.rel_err(cc.grad.cpu().numpy(), cd.grad.numpy()) < 1e-3
