@@ -20,10 +20,15 @@ SIGNATURES = {
     "acfm_last_error_string": [],
     "acfm_project_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_f, _c_f, _c_vp, _c_vp],
     "acfm_project_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp, _c_vp],
+    "acfm_skin_project_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_f, _c_f, _c_vp,
+                              _c_vp, _c_vp],
+    "acfm_skin_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_fwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int,
                         _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "acfm_mask_sums_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_mask_sums_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_raster_fwd_launch_info": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],
 }
 
@@ -71,6 +76,10 @@ def ptr(t):
 def stream_of(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
+
+# optional callable(name, phase) invoked right before (0) / after (1) a dominant kernel's launch; bench.py records
+# CUDA events in it to time that kernel on its own stream inside the timed region
+event_hook = None
 
 # count of kernels launched through the C ABI by this process (bench.py reports it)
 launches = 0

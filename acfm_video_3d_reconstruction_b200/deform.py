@@ -1,0 +1,103 @@
+"""Handle-based deformation of the template ("LBS") — drop-in for the block the reference inlines in
+ShapeTrainer.forward (/root/reference/multiframe/main.py:586-609, monocular/main.py:203-218) and
+MeshPredictor.forward (multiframe/nnutils/predictor.py:257-276).
+
+The reference factorises B*T identical V x V systems per step.  Because
+  L^T L m + A^T (A m + D) = (L^T L + A^T A) m + A^T D,
+the solve collapses to pred_v = mean_v + W D with W = (L^T L + A^T A)^-1 A^T: one
+V x V Cholesky per step (torch, differentiable w.r.t. the handle weights), then a fused sm_100a kernel
+for the per-frame contraction and the camera-multiplex projection.
+"""
+import torch
+
+from . import _lib
+from . import functional as F_
+
+
+def skinning_matrix(lbs, L):
+    """lbs (V,Kh): softmax-over-vertices handle weights (MeshNet.get_lbs, mesh_net.py:597-599);
+    L (V,V): dense mesh Laplacian (geom_utils.mesh_laplacian).  Returns W (V,Kh)."""
+    A = lbs.t()                                     # (Kh,V), as `self.lbs` in main.py:586
+    M = L.t().matmul(L) + A.t().matmul(A)           # A_augm, main.py:605
+    u = torch.linalg.cholesky(M)
+    return torch.cholesky_solve(A.t(), u)           # (V,Kh)
+
+
+class _SkinProject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean_v, W, delta, cams, offset_z, sx, sy, z_add):
+        _lib.require_cuda(mean_v, W, delta, cams)
+        mean_v, W, delta = F_._f32c(mean_v), F_._f32c(W), F_._f32c(delta)
+        V, Kh = W.shape
+        NB = delta.shape[0]
+        if mean_v.shape != (V, 3) or delta.shape != (NB, Kh, 3):
+            raise ValueError(f"expected mean_v (V,3), W (V,Kh), delta (NB,Kh,3); got {tuple(mean_v.shape)}, "
+                             f"{tuple(W.shape)}, {tuple(delta.shape)}")
+        dev = mean_v.device
+        pred_v = torch.empty((NB, V, 3), dtype=torch.float32, device=dev)
+        ndc, G = None, 0
+        if cams is not None:
+            cams = F_._f32c(cams)
+            if cams.dim() != 2 or cams.shape[1] != 7 or NB == 0 or cams.shape[0] % NB:
+                raise ValueError(f"cams must be (G*NB,7), got {tuple(cams.shape)} for NB={NB}")
+            G = cams.shape[0] // NB
+            ndc = torch.empty((G * NB, V, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.lib().acfm_skin_project_fwd(_lib.ptr(mean_v), _lib.ptr(W), _lib.ptr(delta), _lib.ptr(cams), NB, G,
+                                                  V, Kh, offset_z, sx, sy, z_add, _lib.ptr(pred_v), _lib.ptr(ndc),
+                                                  _lib.stream_of(mean_v))
+        _lib.check(st, "acfm_skin_project_fwd")
+        _lib.count()
+        ctx.save_for_backward(W, delta, cams, pred_v)
+        ctx.sx, ctx.sy = sx, sy
+        if ndc is None:
+            return pred_v
+        return pred_v, ndc
+
+    @staticmethod
+    def backward(ctx, g_pred, g_ndc=None):
+        W, delta, cams, pred_v = ctx.saved_tensors
+        NB, V, _ = pred_v.shape
+        Kh = W.shape[1]
+        dev = pred_v.device
+        L = _lib.lib()
+        gp = None
+        g_cams = None
+        with torch.cuda.device(dev):
+            if cams is not None and g_ndc is not None:
+                gp = torch.empty_like(pred_v)
+                g_cams = torch.empty_like(cams) if ctx.needs_input_grad[3] else None
+                st = L.acfm_project_bwd(_lib.ptr(pred_v), _lib.ptr(cams), _lib.ptr(F_._f32c(g_ndc)), cams.shape[0], NB, V,
+                                        ctx.sx, ctx.sy, _lib.ptr(gp), _lib.ptr(g_cams), _lib.stream_of(pred_v))
+                _lib.check(st, "acfm_project_bwd")
+                _lib.count()
+            if g_pred is not None:
+                gp = F_._f32c(g_pred) if gp is None else gp + g_pred
+            if gp is None:
+                return None, None, None, g_cams, None, None, None, None
+            g_mean = torch.empty((V, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+            g_W = torch.empty_like(W) if ctx.needs_input_grad[1] else None
+            g_delta = torch.empty_like(delta) if ctx.needs_input_grad[2] else None
+            st = L.acfm_skin_bwd(_lib.ptr(W), _lib.ptr(delta), _lib.ptr(gp), NB, V, Kh, _lib.ptr(g_delta), _lib.ptr(g_W),
+                                 _lib.ptr(g_mean), _lib.stream_of(pred_v))
+            _lib.check(st, "acfm_skin_bwd")
+            _lib.count(2)
+        return g_mean, g_W, g_delta, g_cams, None, None, None, None
+
+
+def deform(mean_v, W, delta_v):
+    """pred_v (NB,V,3) = mean_v + W @ delta_v[b]  — the result of the reference's cholesky_solve (main.py:607-608)."""
+    return _SkinProject.apply(mean_v, W, delta_v, None, 0.0, 1.0, 1.0, 0.0)
+
+
+def deform_and_project(mean_v, W, delta_v, cams, offset_z=0.0, sx=-1.0, sy=-1.0, z_add=F_.EYE_Z):
+    """Fused deformation + G-hypothesis projection.  cams (G*NB,7) hypothesis-major as in main.py:578.
+    Returns pred_v (NB,V,3) and the rasterizer-space vertices ndc (G*NB,V,3) that
+    NeuralRenderer.to_ndc(pred_v.repeat(G,1,1), cams) would produce."""
+    return _SkinProject.apply(mean_v, W, delta_v, cams, float(offset_z), float(sx), float(sy), float(z_add))
+
+
+def handle_deform_reference_form(mean_v, lbs, L, delta_v_res):
+    """Same inputs as the reference block: mean_v (V,3), lbs (V,Kh) = model.get_lbs(), L (V,V),
+    delta_v_res (NB,Kh,3) -> pred_v (NB,V,3)."""
+    return deform(mean_v, skinning_matrix(lbs, L), delta_v_res)

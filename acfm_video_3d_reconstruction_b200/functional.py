@@ -102,6 +102,8 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
     dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
     bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if want_bary else None
     mask = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_mask else None
+    if _lib.event_hook is not None:
+        _lib.event_hook("raster_fwd", 0)
     with torch.cuda.device(dev):
         st = _lib.lib().acfm_raster_fwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K,
                                         float(blur_radius), int(clip_barycentric_coords), int(cull_backfaces),
@@ -109,6 +111,8 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
                                         _lib.ptr(mask), _lib.stream_of(ndc))
     _lib.check(st, "acfm_raster_fwd")
     _lib.count()
+    if _lib.event_hook is not None:
+        _lib.event_hook("raster_fwd", 1)
     return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask)
 
 

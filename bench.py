@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — render fwd+bwd frames/s of the ACFM hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C4]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic input on every rank:
+  skinning matrix (one V x V solve) -> fused handle deformation + G-hypothesis projection -> tile-binned soft
+  rasterizer (fragments pix_to_face/zbuf/dists materialised, fused silhouette blend) -> fused mask losses
+  (l1 + edt) -> hypothesis softmax weighting -> backward to handle offsets, cameras and handle weights ->
+  (N > 1) NCCL all-reduce of the shared-parameter gradients.
+Workload at N=1 is BASELINE.json configs[1] (C2): bird template 642 v / 1280 f, batch 64 frames x 8 camera
+hypotheses = 512 renders of 256 x 256, K = 20, 32 handles.  Weak scaling: every rank owns its own 64 frames.
+`value` = renders of all ranks / max-over-ranks device time, inputs resident in HBM.  `e2e` = the same through the
+public API with host (pinned) inputs copied in and the loss + gradients copied out inside the timed region.
+`--impl reference` times the CPU oracle (restated PyTorch3D 0.3.0 CPU algorithm; the real wheel is not installable)
+on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (template, frames/rank, G, handles, img, K, offset_z)
+    "C2": dict(template="bird", frames=64, G=8, handles=32, img=256, K=20, offset_z=5.0,
+               desc="C2 monocular bird step: 642v/1280f, batch 64 x 8 camera hypotheses = 512 renders/GPU, 256x256, K=20, 32 handles"),
+    "C4": dict(template="ico4", frames=4, G=2, handles=32, img=512, K=50, offset_z=0.0,
+               desc="C4 high-res stress: 2562v/5120f icosphere, 8 renders/GPU, 512x512, K=50"),
+}
+W_EDT = 0.1  # edt_reg_wt-like weight on the edt term (any fixed weight exercises the same kernels)
+
+
+def alg_bytes(img, K, V, F):
+    """Algorithmic HBM bytes per render of the rasterizer, BASELINE.md §3 (API-parity mode)."""
+    fwd = img * img * (16 * K + 4) + 12 * V + 24 * F
+    bwd = img * img * (12 * K + 8) + 24 * V + 24 * F
+    return fwd, bwd
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.1]
+        window = "timed"
+        if len(rows) < 3:
+            rows, window = self.rows, "warmup+timed"
+        sm, mx, reasons = [], [], set()
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the step
+# ---------------------------------------------------------------------------------------------------------------
+class HotPath:
+    """Device-resident constants of one rank's shard + the step itself (public API of the package only)."""
+
+    def __init__(self, cfg, rank, device):
+        from acfm_video_3d_reconstruction_b200 import synthetic
+        self.cfg, self.device = cfg, device
+        wl = synthetic.Workload(cfg["template"], cfg["frames"], cfg["G"], cfg["handles"], cfg["img"], seed=rank,
+                                offset_z=cfg["offset_z"])
+        self.wl = wl
+        self.mean_v = wl.mean_v.to(device)
+        self.lbs_param = wl.lbs_param.to(device).requires_grad_(True)
+        self.L = wl.L.to(device)
+        self.faces = wl.faces.to(device)[None]                     # shared topology, (1,F,3) int64
+        # host-side (pinned) per-step inputs
+        self.h_delta = wl.delta.pin_memory()
+        self.h_cams = wl.cams.pin_memory()
+        tgt, edt = self._targets(rank)
+        self.h_target, self.h_edt = tgt.pin_memory(), edt.pin_memory()
+        self.h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+        self.h_gdelta = torch.empty_like(wl.delta).pin_memory()
+        self.h_gcams = torch.empty_like(wl.cams).pin_memory()
+
+    def _targets(self, rank):
+        """mask_gt = our own render of an independently drawn pose, thresholded; edt = scipy EDT of it (setup only)."""
+        from scipy.ndimage import distance_transform_edt
+        from acfm_video_3d_reconstruction_b200 import NeuralRenderer, synthetic
+        cfg = self.cfg
+        with torch.no_grad():
+            cams = synthetic.cameras(cfg["frames"], 1, seed=1000 + rank).to(self.device)
+            r = NeuralRenderer(cfg["img"], offset_z=cfg["offset_z"])
+            r.faces_per_pixel = cfg["K"]
+            m, _ = r(self.mean_v[None].repeat(cfg["frames"], 1, 1), self.faces.expand(cfg["frames"], -1, -1), cams)
+            tgt = (m > 0.5).float().cpu()
+        edt = torch.from_numpy(np.stack([distance_transform_edt(1 - t.numpy()) for t in tgt]).astype(np.float32))
+        return tgt, edt
+
+    def h2d(self):
+        d = self.device
+        return (self.h_delta.to(d, non_blocking=True), self.h_cams.to(d, non_blocking=True),
+                self.h_target.to(d, non_blocking=True), self.h_edt.to(d, non_blocking=True))
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.h_delta, self.h_cams, self.h_target, self.h_edt))
+
+    def d2h_bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.h_loss, self.h_gdelta, self.h_gcams))
+
+    def step(self, delta, cams, target, edt, world=1):
+        from acfm_video_3d_reconstruction_b200 import deform, loss_utils
+        from acfm_video_3d_reconstruction_b200 import functional as F_
+        cfg = self.cfg
+        delta = delta.detach().requires_grad_(True)
+        cams = cams.detach().requires_grad_(True)
+        self.lbs_param.grad = None
+        lbs = torch.softmax(self.lbs_param, dim=0)                 # MeshNet.get_lbs: softmax over vertices
+        W = deform.skinning_matrix(lbs, self.L)
+        _, ndc = deform.deform_and_project(self.mean_v, W, delta, cams, offset_z=cfg["offset_z"])
+        mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
+        ls = loss_utils.mask_losses(mask, target, edt)
+        per = (ls["l1"] + W_EDT * ls["edt"]).view(cfg["G"], cfg["frames"])
+        probs = torch.softmax(-per, dim=0).detach()                # hypothesis weighting, multiframe/main.py:735-746
+        total = (per * probs).sum(0).mean()
+        total.backward()
+        if world > 1:
+            torch.distributed.all_reduce(self.lbs_param.grad)      # shared-parameter gradient
+        return total.detach(), delta.grad, cams.grad
+
+
+def run_ours(args):
+    from acfm_video_3d_reconstruction_b200 import _lib
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=device)
+    cfg = WORKLOADS[args.workload]
+    hp = HotPath(cfg, rank, device)
+    N_r = cfg["frames"] * cfg["G"]
+    fwd_b, bwd_b = alg_bytes(cfg["img"], cfg["K"], hp.wl.V, hp.wl.F)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # per-kernel events for the roofline of the dominant kernel (the forward rasterizer)
+    kev = []
+    _lib.event_hook = lambda name, phase: kev.append((name, phase, _rec()))
+
+    def _rec():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    dev_in = hp.h2d()
+    torch.cuda.synchronize()
+    clocks = Clocks(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        hp.step(*dev_in, world=world)
+    kev.clear()
+    # ---- timed: device-resident inputs ------------------------------------------------------------------------
+    barrier()
+    launches0 = _lib.launches
+    t0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        hp.step(*dev_in, world=world)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launches - launches0
+    _lib.event_hook = None
+    k_ms = [a[2].elapsed_time(b[2]) for a, b in zip(kev[0::2], kev[1::2]) if a[0] == "raster_fwd"]
+    clk = clocks.stop(t0, t1) if clocks else None
+    # ---- timed: end to end (pinned host -> device -> host) ----------------------------------------------------
+    for _ in range(2):
+        hp.step(*hp.h2d(), world=world)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        loss, gd, gc = hp.step(*hp.h2d(), world=world)
+        hp.h_loss.copy_(loss, non_blocking=True)
+        hp.h_gdelta.copy_(gd, non_blocking=True)
+        hp.h_gcams.copy_(gc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                  # the caller reads the loss every step
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    k_avg = float(np.mean(k_ms)) if k_ms else None
+    achieved = fwd_b * N_r / (k_avg * 1e-3) / 1e9 if k_avg else None
+    out = {
+        "metric": "render fwd+bwd frames/sec (x camera hyps)", "value": N_r * world * args.steps / (ms * 1e-3),
+        "unit": "renders/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "renders_per_gpu": N_r, "fragments": "materialised (API-parity mode)",
+                   "l2": "per-step working set %.1f GB >> 126 MB L2 (no explicit flush)" % ((fwd_b + bwd_b) * N_r / 1e9),
+                   "parallelism": f"dp{world} (frames sharded, NCCL all-reduce of shared-parameter grads)"},
+        "e2e": {"value": N_r * world * args.steps / (ms_e2e * 1e-3), "unit": "renders/s",
+                "h2d_bytes_per_step": hp.h2d_bytes(), "d2h_bytes_per_step": hp.d2h_bytes()},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "raster_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_launch": fwd_b * N_r, "avg_launch_ms": k_avg, "launches_timed": len(k_ms)},
+        "clocks": clk,
+    }
+    traffic = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic):
+        try:
+            out["roofline"]["traffic"] = json.load(open(traffic)).get(args.workload, {}).get("raster_fwd_kernel")
+        except Exception:
+            pass
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(cfg, hp.wl, max_seconds=20.0)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arms (the oracle as checker-turned-baseline: the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_step(wl, cfg, idx, threads):
+    """fwd (project, view, naive raster, blend) + bwd (blend, raster, scatter) of `idx` renders on the host."""
+    from oracle import pt3d_oracle as orc
+    X = wl.mean_v.numpy()[None].repeat(len(idx), 0)
+    cams = wl.cams.numpy()[idx]
+    faces = wl.faces.numpy()[None].repeat(len(idx), 0)
+    fr = orc.neural_renderer_mask(X, faces, cams, img_size=cfg["img"], offset_z=cfg["offset_z"], K=cfg["K"], threads=threads)
+    gm = np.sign(fr["mask"] - 0.5).astype(np.float32) / fr["mask"][0].size
+    orc.neural_renderer_mask_backward(fr, faces, gm)
+
+
+def cpu_baseline(cfg, wl, max_seconds=20.0):
+    from oracle import pt3d_oracle as orc
+    threads = orc.max_threads()
+    n = max(4, min(wl.cams.shape[0], 2 * threads))
+    t = time.time()
+    _oracle_step(wl, cfg, list(range(2)), threads)  # page-in / thread pool warm-up + cost estimate
+    est = (time.time() - t) / 2
+    n = int(max(2, min(n, max_seconds / max(est, 1e-6))))
+    t = time.time()
+    _oracle_step(wl, cfg, list(range(n)), threads)
+    dt = time.time() - t
+    return {"value": n / dt, "unit": "renders/s", "cores": threads, "kind": "port",
+            "sample": f"{n} renders of the same workload (project + naive O(pixels x faces) raster + blend, fwd+bwd), "
+                      f"oracle/ restatement of PyTorch3D 0.3.0's CPU path, OpenMP over (render,row), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from acfm_video_3d_reconstruction_b200 import synthetic
+    from oracle import pt3d_oracle as orc
+    orc.build()
+    cfg = WORKLOADS[args.workload]
+    wl = synthetic.Workload(cfg["template"], cfg["frames"], cfg["G"], cfg["handles"], cfg["img"], seed=0, offset_z=cfg["offset_z"])
+    threads = orc.max_threads()
+    n = max(2, min(threads, 16))
+    idx = list(range(n))
+    for _ in range(args.warmup):
+        _oracle_step(wl, cfg, idx[:2], threads)
+    t = time.time()
+    for _ in range(args.steps):
+        _oracle_step(wl, cfg, idx, threads)
+    dt = time.time() - t
+    val = n * args.steps / dt
+    sample = (f"each step = {n} of the workload's {wl.renders} renders/GPU (bounded sample), restated PyTorch3D 0.3.0 CPU "
+              f"algorithm (oracle/), OpenMP {threads} threads; the real PyTorch3D wheel is not installable offline")
+    print(json.dumps({
+        "impl": "reference", "metric": "render fwd+bwd frames/sec (x camera hyps)", "value": val, "unit": "renders/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "renders_per_step_sample": n},
+        "cpu_baseline": {"value": val, "unit": "renders/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "renders/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,24 @@ int acfm_project_bwd(const float* verts, const float* cams, const float* grad_ou
                      int V, float sx, float sy, float* grad_verts, float* grad_cams, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Handle deformation ("LBS") fused with the camera-multiplex projection.  Replaces the inlined
+ * deformation block (multiframe/main.py:586-609; monocular/main.py:203-218;
+ * multiframe/nnutils/predictor.py:257-276) after its algebraic collapse
+ *   pred_v = mean_v + W delta,  W = (L^T L + A^T A)^-1 A^T  (V,Kh)      
+ * and the G-fold `pred_v.repeat(G,1,1)` + projection that follows (main.py:609,623-625).
+ *   mean_v (V,3), W (V,Kh) row-major, delta (NB,Kh,3), cams (G*NB,7) hypothesis-major (n = g*NB + b)
+ *   pred_v (NB,V,3) or NULL;  ndc (G*NB,V,3) or NULL (same view flags as acfm_project_fwd).
+ * --------------------------------------------------------------------------------------------- */
+int acfm_skin_project_fwd(const float* mean_v, const float* W, const float* delta, const float* cams,
+                          int NB, int G, int V, int Kh, float offset_z, float sx, float sy, float z_add,
+                          float* pred_v, float* ndc, void* stream);
+
+/* grad_pred_v (NB,V,3) -> grad_delta (NB,Kh,3), grad_W (V,Kh), grad_mean_v (V,3); each may be NULL.
+ * (The projection part of the backward is acfm_project_bwd with NB-broadcast verts.) */
+int acfm_skin_bwd(const float* W, const float* delta, const float* grad_pred_v, int NB, int V, int Kh,
+                  float* grad_delta, float* grad_W, float* grad_mean_v, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Rasterization.  Replaces pytorch3d.renderer.mesh.rasterize_meshes (PyTorch3D 0.3.0, the
  * reference's third-party dependency) as reached through MeshRasterizer from
  * NeuralRenderer.forward (multiframe/nnutils/nmr.py:152-171 soft, K=20;  :173-196 hard, K=1,
@@ -78,6 +96,19 @@ int acfm_raster_soft_bwd(const float* ndc, const void* faces, int faces_i64,
                          int64_t faces_batch_stride, int N, int V, int F, int H, int W, int K,
                          float sigma, const int64_t* pix_to_face, const float* dists,
                          const float* mask, const float* grad_mask, float* grad_ndc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused per-render mask losses.  Replaces loss_utils.l1_loss / iou_loss / edt_loss
+ * (multiframe/nnutils/loss_utils.py:18-32,72-77,245-253) and the callers' G-fold target repeats
+ * (multiframe/main.py:644,716).  mask (N,HW); target, edt (NB,HW) read at n % NB (edt may be NULL);
+ *   sums[n] = { sum|m-t|, sum m*t, sum(m+t-m*t), sum edt*m }   (N,4)
+ * l1 = sums0/HW; iou_loss = 1 - sums1/(sums2+1e-6); edt_loss = sums3/HW are formed by the host wrapper.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_mask_sums_fwd(const float* mask, const float* target, const float* edt, int N, int NB, int HW,
+                       float* sums, void* stream);
+/* grad_sums (N,4) -> grad_mask (N,HW) = g0*sign(m-t) + g1*t + g2*(1-t) + g3*edt */
+int acfm_mask_sums_bwd(const float* mask, const float* target, const float* edt, const float* grad_sums,
+                       int N, int NB, int HW, float* grad_mask, void* stream);
 
 /* Query: dynamic shared memory (bytes) and CTAs the forward rasterizer launches for a shape
  * (host-only helper used by bench.py for the launch/roofline accounting). */
