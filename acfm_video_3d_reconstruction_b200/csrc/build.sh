@@ -15,5 +15,5 @@ for s in "${SRCS[@]}"; do
   fi
   OBJS+=("$o")
 done
-"$NVCC" -shared -o ../libacfm_b200.so "${OBJS[@]}" -ccbin /usr/bin/g++ -lcudart
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o ../libacfm_b200.so "${OBJS[@]}" -ccbin /usr/bin/g++ -lcudart
 echo "built $(cd .. && pwd)/libacfm_b200.so"

@@ -50,6 +50,7 @@ class _SkinProject(torch.autograd.Function):
         _lib.count()
         ctx.save_for_backward(W, delta, cams, pred_v)
         ctx.sx, ctx.sy = sx, sy
+        ctx.set_materialize_grads(False)
         if ndc is None:
             return pred_v
         return pred_v, ndc

@@ -125,6 +125,7 @@ class _SoftSilhouette(torch.autograd.Function):
         ctx.save_for_backward(ndc.contiguous(), faces, fr["pix_to_face"], fr["dists"], fr["mask"])
         ctx.cfg = (int(image_size), int(K), float(sigma))
         ctx.mark_non_differentiable(fr["pix_to_face"], fr["zbuf"], fr["dists"])
+        ctx.set_materialize_grads(False)
         return fr["mask"], fr["pix_to_face"], fr["zbuf"], fr["dists"]
 
     @staticmethod
@@ -133,6 +134,8 @@ class _SoftSilhouette(torch.autograd.Function):
         S, K, sigma = ctx.cfg
         N, V, _ = ndc.shape
         fa, i64, fstride, F = _faces_arg(faces, N)
+        if grad_mask is None:
+            return None, None, None, None, None, None
         grad_mask = _f32c(grad_mask)
         g = torch.empty_like(ndc)
         with torch.cuda.device(ndc.device):

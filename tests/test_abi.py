@@ -42,7 +42,7 @@ def test_bad_arguments_return_status_not_crash():
     assert st == 1
     smem, ctas, thr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     assert lib.acfm_raster_fwd_launch_info(512, 642, 1280, 256, 256, 20, smem, ctas, thr) == 0
-    assert ctas.value == 512 * 16 and thr.value in (128, 256) and 0 < smem.value <= 227 * 1024
+    assert ctas.value == 512 * 64 and thr.value in (128, 256) and 0 < smem.value <= 227 * 1024
 
 
 def test_cpu_tensors_are_refused():
