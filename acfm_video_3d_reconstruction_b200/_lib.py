@@ -27,6 +27,16 @@ SIGNATURES = {
                         _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+    "acfm_raster_dists_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,
+                              _c_vp, _c_vp, _c_vp],
+    "acfm_shade_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int,
+                       _c_int, _c_vp, _c_int, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_vp, _c_vp],
+    "acfm_shade_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int,
+                       _c_int, _c_vp, _c_int, _c_i64, _c_f, _c_f, _c_f, _c_f, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp],
+    "acfm_camera_assemble_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_f, _c_vp, _c_vp],
+    "acfm_camera_assemble_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_f, _c_vp, _c_vp],
+    "acfm_uv_sample_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_uv_sample_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_mask_sums_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_mask_sums_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_raster_fwd_launch_info": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],

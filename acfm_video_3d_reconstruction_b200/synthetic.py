@@ -105,6 +105,22 @@ def cameras(num_frames, G, seed=0):
     return torch.cat(out, 0).float()
 
 
+def uv_sampler(verts, faces, tex_size=6):
+    """compute_uvsampler + get_spherical_coords (utils/mesh.py:197-238 of the reference): per-face T x T
+    barycentric sample points pushed to spherical UV in [-1,1].  Returns (F, T, T, 2) float32."""
+    a = np.arange(tex_size, dtype=np.float64) / (tex_size - 1)
+    coords = np.stack([(x, y) for x in a for y in a])                       # itertools.product(alpha, beta)
+    vs = verts[faces].astype(np.float64)
+    v2, v0v2, v1v2 = vs[:, 2], vs[:, 0] - vs[:, 2], vs[:, 1] - vs[:, 2]
+    samples = np.dstack([v0v2, v1v2]).dot(coords.T) + v2.reshape(-1, 3, 1)  # F x 3 x T*T
+    X = np.transpose(samples, (0, 2, 1)).reshape(-1, 3)
+    rad = np.linalg.norm(X, axis=1)
+    theta = np.arccos(np.clip(X[:, 2] / np.maximum(rad, 1e-12), -1, 1))
+    phi = np.arctan2(X[:, 1], X[:, 0])
+    uv = np.stack([((phi + np.pi) / (2 * np.pi)) * 2 - 1, (theta / np.pi) * 2 - 1], 1)
+    return uv.reshape(-1, tex_size, tex_size, 2).astype(np.float32)
+
+
 class Workload:
     """One data-parallel shard of a training step's hot-path inputs (host tensors)."""
 

@@ -97,6 +97,57 @@ int acfm_raster_soft_bwd(const float* ndc, const void* faces, int faces_i64,
                          float sigma, const int64_t* pix_to_face, const float* dists,
                          const float* mask, const float* grad_mask, float* grad_ndc, void* stream);
 
+/* Backward of rasterize_meshes for an upstream gradient on dists only (grad_dists (N,H,W,K)); used by the
+ * texture branch.  Gradients on zbuf / bary are not propagated: the reference's callers render textures
+ * from detached vertices (multiframe/main.py:627,634) and TexturesAtlas sampling is piecewise constant. */
+int acfm_raster_dists_bwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
+                          int N, int V, int F, int H, int W, int K, const int64_t* pix_to_face,
+                          const float* dists, const float* grad_dists, float* grad_ndc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Texture branch shading.  Replaces TexturesAtlas.sample_textures / Textures(verts_rgb) interpolation,
+ * SoftPhongShader with ambient-only lights and softmax_rgb_blend (PyTorch3D 0.3.0) as used by
+ * NeuralRenderer.forward(textures=...) (multiframe/nnutils/nmr.py:173-200).
+ *   mode 0: tex = atlas (N*F,R,R,3) indexed by packed face id;  mode 1: tex = vertex colours (NC,V,3),
+ *           render n uses tex[n % NC], with faces as in acfm_raster_fwd.
+ *   rgba (N,H,W,4): rgb = softmax-blended colour (background 0), a = 1 - prod(1 - prob).   K <= 8.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_shade_fwd(const int64_t* pix_to_face, const float* bary, const float* dists, const float* zbuf,
+                   int N, int H, int W, int K, int mode, const float* tex, int R, int V, int F, int NC,
+                   const void* faces, int faces_i64, int64_t faces_batch_stride, float sigma, float gamma,
+                   float znear, float zfar, float* rgba, void* stream);
+/* grad_rgba (N,H,W,4) -> grad_tex (same shape as tex, grad_tex_numel floats, zeroed here) and, if not NULL,
+ * grad_dists (N,H,W,K) (through prob; feed it to acfm_raster_dists_bwd). */
+int acfm_shade_bwd(const int64_t* pix_to_face, const float* bary, const float* dists, const float* zbuf,
+                   int N, int H, int W, int K, int mode, const float* tex, int R, int V, int F, int NC,
+                   const void* faces, int faces_i64, int64_t faces_batch_stride, float sigma, float gamma,
+                   float znear, float zfar, const float* grad_rgba, float* grad_tex, int64_t grad_tex_numel,
+                   float* grad_dists, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Camera-multiplex assembly.  Replaces multiframe/main.py:573-584 with mirror_cameras (:113-125) and
+ * transform_cameras (:128-138).  raw, out (N = G*NB, 7) hypothesis-major; mirror_flag (NB) 0/1 floats or NULL;
+ * transforms (NB,4) = [a, bx, by, flag] or NULL, both read at n % NB.
+ *   s = relu(scale_lr_decay*raw0 + 1) + 1e-12;  q = raw[3:7] / max(|raw[3:7]|, 1e-12);
+ *   mirror: tx -> -tx, q -> standardize((0,0,1,0) (x) standardize(q));  transform: s*a, t*a + b.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_camera_assemble_fwd(const float* raw, const float* mirror_flag, const float* transforms, int N,
+                             int NB, float scale_lr_decay, float* out, void* stream);
+int acfm_camera_assemble_bwd(const float* raw, const float* mirror_flag, const float* transforms,
+                             const float* grad_out, int N, int NB, float scale_lr_decay, float* grad_raw,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Texture-flow UV sampling.  Replaces the grid_sample + permute + tanh of TexturePredictorUV.forward
+ * (multiframe/nnutils/mesh_net.py:169-172).  uvimage (B,C,Hu,Wu); grid (P,2) in [-1,1] shared by all
+ * frames (P = F*T*T); out (B,P,C) = bilinear(align_corners=True, zero padding), then (tanh+1)/2 if
+ * apply_tanh.  Backward takes the saved output; grad_uvimage (B,C,Hu,Wu) is zeroed here.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_uv_sample_fwd(const float* uvimage, const float* grid, int B, int C, int Hu, int Wu, int P,
+                       int apply_tanh, float* out, void* stream);
+int acfm_uv_sample_bwd(const float* out, const float* grid, const float* grad_out, int B, int C, int Hu,
+                       int Wu, int P, int apply_tanh, float* grad_uvimage, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused per-render mask losses.  Replaces loss_utils.l1_loss / iou_loss / edt_loss
  * (multiframe/nnutils/loss_utils.py:18-32,72-77,245-253) and the callers' G-fold target repeats

@@ -199,6 +199,19 @@ def hard_raster(vertices, faces, cams, img_size=256, offset_z=0.0, dtype=np.floa
     return fr
 
 
+def vertex_colors_as_texels(fr, colors, faces):
+    """Textures(verts_rgb) interpolation with the (clipped) barycentrics: texel (N,H,W,K,3)."""
+    p2f, bary = fr["pix_to_face"], fr["bary"]
+    N, F = faces.shape[0], faces.shape[1]
+    m = p2f >= 0
+    fi = np.where(m, p2f, 0)
+    n_idx, f_idx = fi // F, fi % F
+    cols = np.broadcast_to(colors, (N,) + colors.shape[-2:])
+    vid = faces[n_idx, f_idx]                                      # (N,H,W,K,3)
+    c = cols[n_idx[..., None], vid]                                # (N,H,W,K,3 verts,3 rgb)
+    return (bary[..., None] * c).sum(-2) * m[..., None]
+
+
 def atlas_shade(fr, atlas, sigma=SIGMA, gamma=1e-4, znear=1.0, zfar=100.0, eps=1e-10):
     """TexturesAtlas.sample_textures + ambient-only Phong + softmax_rgb_blend: SURVEY.md §9.7.
     atlas (N,F,T,T,3).  Returns imgs (N,3,H,W), sil (N,H,W)."""
@@ -210,13 +223,22 @@ def atlas_shade(fr, atlas, sigma=SIGMA, gamma=1e-4, znear=1.0, zfar=100.0, eps=1
     m = p2f >= 0
     b = bary[..., :2].astype(dt)
     wxy = np.floor(b * dt.type(R)).astype(np.int64)
-    below = ((b * dt.type(R)).sum(-1) - wxy.sum(-1).astype(dt)) <= 1.0
+    # TexturesAtlas.sample_textures: below_diag = (bary_w01.sum(-1) * R - w_xy.float().sum(-1)) <= 1.0
+    below = (b.sum(-1) * dt.type(R) - wxy.astype(dt).sum(-1)) <= 1.0
     wx = np.where(below, wxy[..., 0], R - 1 - wxy[..., 0])
     wy = np.where(below, wxy[..., 1], R - 1 - wxy[..., 1])
     fi = np.where(m, p2f, 0)
     wx = np.clip(np.where(m, wx, 0), 0, R - 1)
     wy = np.clip(np.where(m, wy, 0), 0, R - 1)
     texel = ap[fi, wy, wx] * m[..., None]                                   # (N,H,W,K,3)
+    return blend_texels(fr, texel, sigma, gamma, znear, zfar, eps)
+
+
+def blend_texels(fr, texel, sigma=SIGMA, gamma=1e-4, znear=1.0, zfar=100.0, eps=1e-10):
+    """softmax_rgb_blend (background 0) of per-fragment colours texel (N,H,W,K,3): SURVEY.md §9.7."""
+    p2f, dists, zbuf = fr["pix_to_face"], fr["dists"], fr["zbuf"]
+    dt = dists.dtype
+    m = p2f >= 0
     prob = (1.0 / (1.0 + np.exp(dists.astype(np.float64) / sigma))).astype(dt) * m
     alpha = np.prod(1.0 - prob, axis=-1)
     zinv = ((zfar - zbuf) / (zfar - znear)).astype(dt) * m

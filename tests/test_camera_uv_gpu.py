@@ -1,0 +1,68 @@
+"""GPU parity: camera-multiplex assembly vs the torch restatement of multiframe/main.py:573-582 (+ mirror /
+transform fix-ups), and the UV texture sampler vs torch.nn.functional.grid_sample (the op the reference calls,
+mesh_net.py:169-172).  Floating-point kernels: tolerance 1e-6 absolute on O(1) values, gradients 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_ref
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_camera_assembly_fwd_bwd():
+    from acfm_video_3d_reconstruction_b200 import camera
+    gen = torch.Generator().manual_seed(0)
+    G, NB = 4, 6
+    raw = torch.randn(G, NB, 7, generator=gen)
+    raw[0, 0, 0] = -40.0                     # relu clamps the scale
+    mirror = (torch.rand(NB, generator=gen) > 0.5).float()
+    tf = torch.cat([torch.rand(NB, 1, generator=gen) + 0.5, torch.randn(NB, 2, generator=gen) * 0.1,
+                    (torch.rand(NB, 1, generator=gen) > 0.5).float()], 1)
+    rd = raw.double().requires_grad_(True)
+    ref = torch_ref.assemble_cameras(rd, mirror.double(), tf.double(), 0.05)
+    w = torch.randn(G * NB, 7, generator=gen)
+    (ref * w.double()).sum().backward()
+    rc = raw.cuda().requires_grad_(True)
+    out = camera.assemble_cameras(rc, mirror.cuda(), tf.cuda(), 0.05)
+    assert out.shape == (G * NB, 7)
+    assert np.abs(out.detach().cpu().numpy() - ref.detach().numpy()).max() < 1e-6
+    (out * w.cuda()).sum().backward()
+    assert util.rel_err(rc.grad.cpu().numpy(), rd.grad.numpy()) < 1e-4
+    # no fix-ups: plain scale / normalise
+    out2 = camera.assemble_cameras(raw.cuda().reshape(-1, 7))
+    ref2 = torch.cat([torch.relu(0.05 * raw[..., :1] + 1) + 1e-12, raw[..., 1:3],
+                      torch.nn.functional.normalize(raw[..., 3:], dim=-1)], -1).reshape(-1, 7)
+    assert np.abs(out2.cpu().numpy() - ref2.numpy()).max() < 1e-6
+
+
+def test_uv_sampler_vs_grid_sample():
+    from acfm_video_3d_reconstruction_b200 import synthetic, texture
+    v, f = util.template("bird")
+    T = 6
+    uvs = torch.from_numpy(synthetic.uv_sampler(v / np.abs(v).max(), f, T))             # (F,T,T,2)
+    uvs[0, 0, 0] = torch.tensor([-1.0, 1.0]); uvs[1, 0, 0] = torch.tensor([1.3, -1.2])   # corners / out of range
+    gen = torch.Generator().manual_seed(1)
+    B, Hu, Wu = 3, 128, 256
+    img = torch.randn(B, 3, Hu, Wu, generator=gen)
+    F = f.shape[0]
+    # the reference's lines (mesh_net.py:169-172)
+    imd = img.double().requires_grad_(True)
+    samp = uvs.view(1, F, T * T, 2).double()
+    tp = torch.nn.functional.grid_sample(imd, samp.repeat(B, 1, 1, 1), align_corners=True)
+    tp = tp.reshape(B, -1, F, T, T).permute(0, 2, 3, 4, 1)
+    tp = (torch.tanh(tp) + 1) / 2
+    w = torch.randn(tp.shape, generator=gen)
+    (tp * w.double()).sum().backward()
+    ic = img.cuda().requires_grad_(True)
+    out = texture.uv_sample(ic, uvs.view(1, F, T * T, 2).cuda())
+    assert out.shape == (B, F, T, T, 3)
+    # values vs the same torch op in fp32 (what the reference executes); fp64 is only the gradient truth, since
+    # the fp32 sample position ((x+1)/2*(W-1)) alone moves the bilinear tap by ~1e-5 pixel
+    tp32 = torch.nn.functional.grid_sample(img, uvs.view(1, F, T * T, 2).repeat(B, 1, 1, 1), align_corners=True)
+    tp32 = (torch.tanh(tp32.reshape(B, -1, F, T, T).permute(0, 2, 3, 4, 1)) + 1) / 2
+    assert np.abs(out.detach().cpu().numpy() - tp32.numpy()).max() < 2e-6
+    assert np.abs(out.detach().cpu().numpy() - tp.detach().numpy()).max() < 1e-4
+    (out * w.cuda()).sum().backward()
+    assert util.rel_err(ic.grad.cpu().numpy(), imd.grad.numpy()) < 1e-4
