@@ -39,6 +39,17 @@ SIGNATURES = {
     "acfm_uv_sample_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_mask_sums_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_mask_sums_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_visible_verts": [_c_vp, _c_i64, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_bds_loss_fwd": [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
+    "acfm_bds_loss_bwd": [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_of_loss_fwd": [_c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp,
+                         _c_vp, _c_vp],
+    "acfm_of_loss_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_kp_loss_fwd": [_c_vp, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_kp_loss_bwd": [_c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_hypothesis_weight_fwd": [_c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
+    "acfm_hypothesis_weight_bwd": [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_laplacian_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_raster_fwd_launch_info": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],
 }
 

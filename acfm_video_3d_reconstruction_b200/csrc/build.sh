@@ -5,12 +5,12 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        -ccbin /usr/bin/g++ --fmad=true -Xptxas -v)
-SRCS=(api.cu project.cu skin.cu camera.cu raster.cu shade.cu uvsample.cu losses.cu)
+SRCS=(api.cu project.cu skin.cu camera.cu raster_fwd.cu raster_bwd.cu shade.cu uvsample.cu losses.cu reproj.cu laplacian.cu)
 OBJS=()
 mkdir -p _obj
 for s in "${SRCS[@]}"; do
   o=_obj/${s%.cu}.o
-  if [[ ! -f $o || $s -nt $o || common.cuh -nt $o || ../../include/acfm_b200.h -nt $o ]]; then
+  if [[ ! -f $o || $s -nt $o || common.cuh -nt $o || raster_common.cuh -nt $o || ../../include/acfm_b200.h -nt $o ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" 2> "_obj/${s%.cu}.ptxas.log" || { cat "_obj/${s%.cu}.ptxas.log" >&2; exit 1; }
   fi
   OBJS+=("$o")

@@ -1,0 +1,225 @@
+// raster_bwd.cu — backward of the rasterizer for gradients on dists, with the soft-silhouette blend
+// backward fused in.  Replaces _C.rasterize_meshes_backward + the autograd of sigmoid_alpha_blend
+// (PyTorch3D 0.3.0) as reached from NeuralRenderer.forward (/root/reference/multiframe/nnutils/nmr.py:143-172).
+// Semantics: SURVEY.md §9.5-9.6.
+#include "common.cuh"
+#include "raster_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Silhouette backward.  One CTA per (render, 32x32 region).  Pixels whose mask is exactly 0 have no
+// fragments (every kept fragment has prob >= ~1e-4) and pixels with zero upstream gradient contribute
+// nothing: both are dropped while the region's pixels are compacted into a shared list, so the fragment
+// tensors of ~87% of the pixels are never read.  A lane then owns one ACTIVE pixel and walks its K
+// fragments starting at a lane-dependent offset, so that neighbouring pixels (which see the same faces
+// at the same depth rank) touch different vertices at the same time: shared-memory float atomics are
+// CAS loops on sm_100 and this keeps them to ~1 iteration.  Gradients reach HBM as one atomicAdd per
+// touched (CTA, vertex, component) instead of PyTorch3D's 4-9 global atomics per fragment.
+// ---------------------------------------------------------------------------------------------
+struct BwdParams {
+  const float* ndc;
+  const void* faces;
+  long long faces_stride;
+  int N, V, F, H, W, K;
+  float sigma;
+  const long long* p2f;
+  const float* dists;
+  const float* mask;
+  const float* grad_mask;
+  const float* grad_dists;  // FROM_MASK == false: upstream gradient per fragment (N,H,W,K)
+  float* grad_ndc;
+  int regions_x, regions_y;
+};
+
+struct BwdSmem {
+  int off_verts, off_faces, off_acc, off_list, total;
+  __host__ __device__ BwdSmem(int V, int F) {
+    int o = 32;
+    off_verts = o; o += ((V * 12 + 16 + 15) / 16) * 16;
+    off_faces = o; o += F * 8;
+    off_acc = o; o += ((V * 8 + 15) / 16) * 16;
+    off_list = o; o += kRegion * kRegion * 2;
+    total = o;
+  }
+};
+
+// d(dist)/d(a), d(dist)/d(b) for the segment ab closest to p (PointLineDistanceBackward, §9.6)
+__device__ __forceinline__ void seg_grad(float px, float py, float ax, float ay, float bx, float by, float g, int ia,
+                                         int ib, float* acc) {
+  const float bax = bx - ax, bay = by - ay;
+  const float l2 = bax * bax + bay * bay;
+  float t = (bax * (px - ax) + bay * (py - ay)) / l2;
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float qx = (1.0f - t) * ax + t * bx, qy = (1.0f - t) * ay + t * by;
+  const float gx = g * 2.0f * (qx - px), gy = g * 2.0f * (qy - py);
+  atomicAdd(acc + ia * 2, (1.0f - t) * gx);
+  atomicAdd(acc + ia * 2 + 1, (1.0f - t) * gy);
+  atomicAdd(acc + ib * 2, t * gx);
+  atomicAdd(acc + ib * 2 + 1, t * gy);
+}
+
+// FROM_MASK: the upstream gradient is d loss / d mask and the blend backward (§9.5) is fused in;
+// otherwise it is d loss / d dists per fragment (texture branch, general rasterize_meshes backward on dists).
+template <typename IdxT, bool FROM_MASK>
+__global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p) {
+  constexpr int NT = 128, NWARPS = 4;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const BwdSmem L(p.V, p.F);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  int* nactive = reinterpret_cast<int*>(smem + 8);
+  int* next_chunk = reinterpret_cast<int*>(smem + 12);
+  ushort4* sfaces = reinterpret_cast<ushort4*>(smem + L.off_faces);
+  float* acc = reinterpret_cast<float*>(smem + L.off_acc);
+  unsigned short* alist = reinterpret_cast<unsigned short*>(smem + L.off_list);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int regions = p.regions_x * p.regions_y;
+  const int n = blockIdx.x / regions;
+  const int rg = blockIdx.x - n * regions;
+  const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
+  const int K = p.K;
+
+  if (tid == 0) { *nactive = 0; *next_chunk = 0; }
+  __syncthreads();
+  // ---- 1. compact the region's active pixels (coalesced reads of mask / grad_mask) -------------------
+  for (int i0 = 0; i0 < kRegion * kRegion; i0 += NT) {
+    const int i = i0 + tid;
+    const int x = px0 + (i & (kRegion - 1)), y = py0 + (i / kRegion);
+    bool act = false;
+    if (x < p.W && y < p.H) {
+      const long long pix = ((long long)n * p.H + y) * p.W + x;
+      if (FROM_MASK) act = (p.mask[pix] != 0.0f) && (p.grad_mask[pix] != 0.0f);
+      else act = p.p2f[pix * K] >= 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(nactive, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (act) alist[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+  }
+  __syncthreads();
+  const int na = *nactive;
+  if (na == 0) return;
+
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  const long long fbase = (long long)n * p.faces_stride;
+  for (int f = tid; f < p.F; f += NT) {
+    const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
+    sfaces[f] = make_ushort4((unsigned short)fp[0], (unsigned short)fp[1], (unsigned short)fp[2], 0);
+  }
+  for (int i = tid; i < p.V * 2; i += NT) acc[i] = 0.0f;
+  __syncthreads();
+  const float* sv = stage_bulk_1d(smem + L.off_verts, p.ndc + (size_t)n * p.V * 3, (uint32_t)p.V * 12u, bar, 0);
+
+  // ---- 2. one active pixel per lane, 32 at a time, chunks pulled dynamically --------------------------
+  const float inv_sigma = 1.0f / p.sigma;
+  const int nchunks = (na + 31) / 32;
+  while (true) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(next_chunk, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= nchunks) break;
+    const int a = c * 32 + lane;
+    if (a >= na) continue;
+    const int i = alist[a];
+    const int xi = px0 + (i & (kRegion - 1)), yi = py0 + (i / kRegion);
+    const long long pix = ((long long)n * p.H + yi) * p.W + xi;
+    const float xf = pix_to_ndc(p.W - 1 - xi, p.W), yf = pix_to_ndc(p.H - 1 - yi, p.H);
+    const long long* pf = p.p2f + pix * K;
+    const float* pd = p.dists + pix * K;
+    float alpha = 1.0f;
+    int cnt = 0;
+    for (; cnt < K; ++cnt) {
+      if (pf[cnt] < 0) break;  // lists are front-packed
+      if (FROM_MASK) alpha *= 1.0f - 1.0f / (1.0f + expf(pd[cnt] * inv_sigma));
+    }
+    float ga = 1.0f;
+    if (FROM_MASK) ga = -p.grad_mask[pix] * alpha * inv_sigma;
+    if (ga == 0.0f || cnt == 0) continue;
+    int k = (lane * 7) % cnt;  // decorrelate neighbouring pixels (see header comment)
+    for (int s = 0; s < cnt; ++s) {
+      const float d = pd[k];
+      const int f = (int)(pf[k] - (long long)n * p.F);
+      float gd;
+      if (FROM_MASK) {
+        // d mask / d dist_k = -(prob_k / sigma) * prod_j (1 - prob_j)   
+        gd = ga * (1.0f / (1.0f + expf(d * inv_sigma)));
+      } else {
+        gd = p.grad_dists[pix * K + k];
+      }
+      k = (k + 1 == cnt) ? 0 : k + 1;
+      if (gd == 0.0f) continue;
+      if (signbit(d)) gd = -gd;  // dist = inside ? -|d| : |d|
+      const ushort4 iv = sfaces[f];
+      const int i0 = iv.x, i1 = iv.y, i2 = iv.z;
+      const float x0 = sv[i0 * 3], y0 = sv[i0 * 3 + 1], x1 = sv[i1 * 3], y1 = sv[i1 * 3 + 1];
+      const float x2 = sv[i2 * 3], y2 = sv[i2 * 3 + 1];
+      const float d01 = point_line_dist(xf, yf, x0, y0, x1, y1);
+      const float d02 = point_line_dist(xf, yf, x0, y0, x2, y2);
+      const float d12 = point_line_dist(xf, yf, x1, y1, x2, y2);
+      if (d01 <= d02 && d01 <= d12) seg_grad(xf, yf, x0, y0, x1, y1, gd, i0, i1, acc);
+      else if (d02 <= d01 && d02 <= d12) seg_grad(xf, yf, x0, y0, x2, y2, gd, i0, i2, acc);
+      else if (d12 <= d01 && d12 <= d02) seg_grad(xf, yf, x1, y1, x2, y2, gd, i1, i2, acc);
+    }
+  }
+  __syncthreads();
+  float* gout = p.grad_ndc + (size_t)n * p.V * 3;
+  for (int i = tid; i < p.V * 2; i += NT) {
+    const float a = acc[i];
+    if (a != 0.0f) atomicAdd(gout + (i >> 1) * 3 + (i & 1), a);
+  }
+}
+
+}  // namespace
+
+namespace {
+int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
+               int N, int V, int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
+               const float* mask, const float* grad_mask, const float* grad_dists, float* grad_ndc, void* stream) {
+  ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0 && K >= 1, ACFM_ERR_BAD_ARG, "%s: bad sizes", who);
+  ACFM_REQUIRE(!from_mask || sigma > 0.0f, ACFM_ERR_BAD_ARG, "%s: sigma must be > 0", who);
+  ACFM_REQUIRE(faces_batch_stride == 0 || faces_batch_stride == (int64_t)F * 3, ACFM_ERR_BAD_ARG, "%s: faces_batch_stride must be 0 or F*3", who);
+  if (N == 0 || V == 0) return ACFM_OK;
+  ACFM_REQUIRE(ndc && faces && pix_to_face && dists && grad_ndc, ACFM_ERR_BAD_ARG, "%s: null pointer", who);
+  ACFM_REQUIRE(from_mask ? (mask && grad_mask) : (grad_dists != nullptr), ACFM_ERR_BAD_ARG, "%s: null gradient pointer", who);
+  ACFM_REQUIRE(F <= 65535 && V <= 65535, ACFM_ERR_UNSUPPORTED, "%s: V=%d, F=%d must be <= 65535", who, V, F);
+  cudaStream_t st = (cudaStream_t)stream;
+  ACFM_CUDA_OK(cudaMemsetAsync(grad_ndc, 0, sizeof(float) * 3 * (size_t)N * V, st));
+  if (F == 0) return ACFM_OK;
+  BwdParams p;
+  p.ndc = ndc; p.faces = faces; p.faces_stride = faces_batch_stride;
+  p.N = N; p.V = V; p.F = F; p.H = H; p.W = W; p.K = K; p.sigma = from_mask ? sigma : 1.0f;
+  p.p2f = (const long long*)pix_to_face; p.dists = dists; p.mask = mask; p.grad_mask = grad_mask; p.grad_dists = grad_dists;
+  p.grad_ndc = grad_ndc;
+  p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
+  const BwdSmem L(V, F);
+  ACFM_REQUIRE(L.total <= 227 * 1024, ACFM_ERR_UNSUPPORTED, "%s: needs %d B of shared memory (max 232448)", who, L.total);
+  const long long ctas = (long long)N * p.regions_x * p.regions_y;
+  ACFM_REQUIRE(ctas < (1ll << 31), ACFM_ERR_UNSUPPORTED, "%s: too many CTAs", who);
+#define ACFM_LAUNCH_BWD(IDX, FM)                                                                                       \
+  do {                                                                                                                 \
+    ACFM_CUDA_OK(cudaFuncSetAttribute(raster_soft_bwd_kernel<IDX, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)); \
+    raster_soft_bwd_kernel<IDX, FM><<<(int)ctas, 128, L.total, st>>>(p);                                               \
+  } while (0)
+  if (faces_i64) { if (from_mask) ACFM_LAUNCH_BWD(long long, true); else ACFM_LAUNCH_BWD(long long, false); }
+  else { if (from_mask) ACFM_LAUNCH_BWD(int, true); else ACFM_LAUNCH_BWD(int, false); }
+#undef ACFM_LAUNCH_BWD
+  ACFM_LAUNCH_OK("raster_soft_bwd_kernel");
+  return ACFM_OK;
+}
+}  // namespace
+
+extern "C" int acfm_raster_soft_bwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
+                                    int N, int V, int F, int H, int W, int K, float sigma, const int64_t* pix_to_face,
+                                    const float* dists, const float* mask, const float* grad_mask, float* grad_ndc,
+                                    void* stream) {
+  return launch_bwd("acfm_raster_soft_bwd", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma,
+                    pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, stream);
+}
+
+extern "C" int acfm_raster_dists_bwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
+                                     int N, int V, int F, int H, int W, int K, const int64_t* pix_to_face,
+                                     const float* dists, const float* grad_dists, float* grad_ndc, void* stream) {
+  return launch_bwd("acfm_raster_dists_bwd", false, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, 0.0f,
+                    pix_to_face, dists, nullptr, nullptr, grad_dists, grad_ndc, stream);
+}

@@ -1,0 +1,768 @@
+// raster_fwd.cu — tile-binned rasterizer forward with the fused soft-silhouette blend.
+//
+// Replaces PyTorch3D 0.3.0 rasterize_meshes (coarse + fine CUDA kernels / naive CPU loop) and
+// SoftSilhouetteShader / sigmoid_alpha_blend as reached from NeuralRenderer.forward
+// (/root/reference/multiframe/nnutils/nmr.py:143-200) and OF_NeuralRenderer.forward (:224-238).
+// Semantics: SURVEY.md §9.2-9.5.  Every value that reaches an output (barycentrics, depth, distances,
+// inside / blur / depth decisions) is computed in strict IEEE fp32 in the CPU reference's operator
+// order, so pix_to_face, zbuf and dists are bit-identical to oracle/.
+//
+// One CTA per (render, 32x32-pixel region):
+//   1. the render's vertices (V*12 B) are staged into shared memory by the TMA unit (cp.async.bulk +
+//      mbarrier); a CTA whose region lies outside the blur-expanded bounding box of the mesh takes the
+//      pure fill path at once (~75% of the CTAs of the reference workloads);
+//   2. all F faces are culled against the region (face-level skips of §9.4 + blur-expanded bbox),
+//      survivors compacted with warp ballots and bucketed front to back by depth;
+//   3. the first `cap` region faces get a RECORD in shared memory, set up once per region: vertices,
+//      barycentric denominator, the refined reciprocals shared by the exact divisions, and three
+//      conservative edge equations (see below);
+//   4. warps pull 8x4-pixel tiles (one pixel per lane) from a shared counter.  Per tile:
+//      (a) scan, lane = face: tile-vs-bbox and tile-vs-edge-equation culling, one ballot per 32 faces;
+//      (b) filter, lane = pixel, face uniform: exact bbox test + conservative edge test (6 FFMA), the
+//          survivors' record ids are pushed on a per-lane queue;
+//      (c) evaluate, lane = pixel, face per lane: each lane pops ITS OWN queue, so lanes only spend
+//          instructions on (pixel, face) pairs that are real candidates (the face-uniform evaluation
+//          of (b)'s survivors would run at ~30% lane utilisation); the exact §9.4 test, then sorted
+//          insertion into the lane's K-nearest list (shared memory, [lane][K|1] layout: conflict-free
+//          both for the lane-private insertions and for the pixel-major output pass);
+//      (d) blend the silhouette in depth order and write pix_to_face / zbuf / dists with 16-byte
+//          stores straight from the lists.
+//   Region faces beyond `cap` (meshes that are tiny on screen) go through a slower face-uniform path
+//   with on-the-fly set-up broadcast by warp shuffles.
+//
+// Conservative edge equations.  For edge i (opposite vertex i) with numerator n_i(p) (w_i = n_i/den),
+// a pixel with sign(den)*n_i(p) < 0 lies outside that edge's line, at distance |n_i|/|e_i| from it and
+// therefore at least that far from the triangle.  g_i(p) = A_i x + B_i y + C_i is n_i normalised by
+// -(|e_i| T), T = 1.001 sqrt(blur) + delta, and shrunk by a bound of its own rounding error, so that
+// g_i(p) < -1 proves "not inside, and squared distance > blur" with margin for the rounding of the exact
+// path: such pixels can never be fragments.  The test only REJECTS; every accepted pair goes through
+// the exact arithmetic.
+//
+// HBM-bound on the API-mandated (N,H,W,K) fragment tensors: 16K+4 bytes written per pixel.
+#include "common.cuh"
+#include "raster_common.cuh"
+
+namespace {
+
+constexpr int kZBuckets = 64;  // depth buckets of the region face list (front-to-back evaluation order)
+constexpr int kQueue = 32;     // per-lane candidate queue depth (record ids, 1 byte each)
+
+struct RasterParams {
+  const float* ndc;
+  const void* faces;
+  long long faces_stride;  // elements between renders (0: shared topology)
+  int N, V, F, H, W, K;
+  float blur, sq_blur, sigma;
+  int clip, cull;
+  long long* p2f;
+  float* zbuf;
+  float* dists;
+  float* bary;
+  float* mask;
+  int regions_x, regions_y;
+  int cap;      // face records per region
+  int vec_ok;   // output pointers are 16-byte aligned
+};
+
+// shared-memory carve-up, identical on host and device
+struct FwdSmem {
+  int off_red, off_hist, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
+  int w_z, w_d, w_f, w_q, w_cnt;  // offsets inside one warp's slab
+  int KS;                         // per-lane list stride (odd)
+  __host__ __device__ FwdSmem(int V, int F, int K, int nwarps, int cap) {
+    int o = 32;  // mbarrier + counters
+    off_red = o; o += nwarps * 32;
+    off_hist = o; o += kZBuckets * 4;
+    off_rlist = o; o += ((F * 2 + 15) / 16) * 16;  // ushort per region face
+    off_recA = o; o += cap * 64;                   // 4 float4 arrays (scan / filter data)
+    off_recB = o; o += cap * 64;                   // 4 float4 arrays (exact evaluation data)
+    off_union = o;
+    off_verts = o;
+    const int vb = ((V * 12 + 16 + 15) / 16) * 16;
+    off_tmp = o + vb;
+    KS = K | 1;
+    int w = 0;
+    w_z = w; w += KS * 32 * 4;
+    w_d = w; w += KS * 32 * 4;
+    w_f = w; w += ((KS * 32 * 2 + 15) / 16) * 16;
+    w_q = w; w += kQueue * 32;
+    w_cnt = w; w += 32;
+    warp_bytes = w;
+    total = off_union + max(nwarps * warp_bytes, vb + F * 4);  // the slabs alias the staging/bucketing scratch
+  }
+};
+
+// fill `total` consecutive fragment slots starting at element `gbase` with the -1 padding
+__device__ __forceinline__ void warp_fill_frag(const RasterParams& p, long long gbase, int total, int lane) {
+  if (p.vec_ok && ((gbase | total) & 3) == 0) {
+    int4* q = reinterpret_cast<int4*>(p.p2f + gbase);
+    const int4 m1 = make_int4(-1, -1, -1, -1);
+    for (int e = lane; e < (total >> 1); e += 32) q[e] = m1;
+    float4* z = reinterpret_cast<float4*>(p.zbuf + gbase);
+    float4* d = reinterpret_cast<float4*>(p.dists + gbase);
+    const float4 f1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+    for (int e = lane; e < (total >> 2); e += 32) { z[e] = f1; d[e] = f1; }
+  } else {
+    for (int e = lane; e < total; e += 32) { p.p2f[gbase + e] = -1; p.zbuf[gbase + e] = -1.f; p.dists[gbase + e] = -1.f; }
+  }
+  if (p.bary) for (int e = lane; e < total * 3; e += 32) p.bary[gbase * 3 + e] = -1.f;
+}
+
+// fill a whole rectangle of pixels [x0,x1) x [y0,y1) of render n (all warps of the CTA)
+template <int NWARPS>
+__device__ __forceinline__ void cta_fill_rect(const RasterParams& p, int n, int x0, int x1, int y0, int y1, int warp, int lane) {
+  const int npx = x1 - x0;
+  for (int y = y0 + warp; y < y1; y += NWARPS) {
+    const long long pix = ((long long)n * p.H + y) * p.W + x0;
+    warp_fill_frag(p, pix * p.K, npx * p.K, lane);
+    if (p.mask) for (int e = lane; e < npx; e += 32) p.mask[pix + e] = 0.0f;
+  }
+}
+
+// ---- the exact per-(pixel, face) test of SURVEY.md §9.4 ---------------------------------------------
+// Inputs: pixel centre, the face's vertices, den = edge(v2,v0,v1)+eps with its refined reciprocal, the
+// refined reciprocals of the squared edge lengths and the "fast division is exact here" flags.
+// Returns false if the pair produces no fragment; else the depth bits and the signed squared distance.
+struct FaceB {
+  float x0, y0, x1, y1, x2, y2, z0, z1, z2, den, yden, r01, r02, r12;
+  int flags;  // face id | den_ok << 16 | l01_ok << 17 | l02_ok << 18 | l12_ok << 19
+};
+
+// generic version: every division individually guarded, degenerate edges handled (rare faces only)
+__device__ __noinline__ bool eval_pair_generic(const FaceB& r, float xf, float yf, int clip, float blur, unsigned& zbits, float& sd) {
+  const float dx0 = fsub(xf, r.x0), dy0 = fsub(yf, r.y0), dx1 = fsub(xf, r.x1), dy1 = fsub(yf, r.y1);
+  const float dx2 = fsub(xf, r.x2), dy2 = fsub(yf, r.y2);
+  const float ex01 = fsub(r.x1, r.x0), ey01 = fsub(r.y1, r.y0), ex02 = fsub(r.x2, r.x0), ey02 = fsub(r.y2, r.y0);
+  const float ex12 = fsub(r.x2, r.x1), ey12 = fsub(r.y2, r.y1);
+  const bool den_ok = r.flags & 0x10000;
+  const float w0 = fdiv_y(fsub(fmul(dx1, ey12), fmul(dy1, ex12)), r.den, r.yden, den_ok);  // edge(p,v1,v2)/den
+  const float w1 = fdiv_y(fsub(fmul(dy2, ex02), fmul(dx2, ey02)), r.den, r.yden, den_ok);  // edge(p,v2,v0)/den
+  const float w2 = fdiv_y(fsub(fmul(dx0, ey01), fmul(dy0, ex01)), r.den, r.yden, den_ok);  // edge(p,v0,v1)/den
+  float c0w = w0, c1w = w1, c2w = w2;
+  if (clip) {
+    c0w = w0 > 0.0f ? w0 : 0.0f; c1w = w1 > 0.0f ? w1 : 0.0f; c2w = w2 > 0.0f ? w2 : 0.0f;
+    float s = fadd(fadd(c0w, c1w), c2w);
+    s = s > 1e-5f ? s : 1e-5f;
+    c0w = fdiv_slow(c0w, s); c1w = fdiv_slow(c1w, s); c2w = fdiv_slow(c2w, s);
+  }
+  float pz = fadd(fadd(fmul(c0w, r.z0), fmul(c1w, r.z1)), fmul(c2w, r.z2));
+  if (pz < 0.0f) return false;
+  const float l01 = fadd(fmul(ex01, ex01), fmul(ey01, ey01));
+  const float l02 = fadd(fmul(ex02, ex02), fmul(ey02, ey02));
+  const float l12 = fadd(fmul(ex12, ex12), fmul(ey12, ey12));
+  const float d01 = point_line_dist_h(dx0, dy0, dx1, dy1, r.x0, r.y0, xf, yf, ex01, ey01, l01, r.r01, r.flags & 0x20000);
+  const float d02 = point_line_dist_h(dx0, dy0, dx2, dy2, r.x0, r.y0, xf, yf, ex02, ey02, l02, r.r02, r.flags & 0x40000);
+  const float d12 = point_line_dist_h(dx1, dy1, dx2, dy2, r.x1, r.y1, xf, yf, ex12, ey12, l12, r.r12, r.flags & 0x80000);
+  const float dist = fminf(fminf(d01, d02), d12);
+  const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
+  if (!inside && dist >= blur) return false;
+  pz = pz + 0.0f;  // canonicalise -0
+  zbits = __float_as_uint(pz);
+  sd = inside ? -dist : dist;
+  return true;
+}
+
+// squared distance from p to q = a + clamp(t) * ba
+__device__ __forceinline__ float seg_dist_t(float t, float ax, float ay, float bax, float bay, float px, float py) {
+  const float tt = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+  const float qx = fadd(ax, fmul(tt, bax)), qy = fadd(ay, fmul(tt, bay));
+  const float dx = fsub(px, qx), dy = fsub(py, qy);
+  return fadd(fmul(dx, dx), fmul(dy, dy));
+}
+
+// Faces flagged kFaceFast (no degenerate edge, every denominator inside the fast-division window; practically all
+// faces) take a straight-line path: p - v_i and the edge vectors, three barycentric quotients behind ONE operand
+// guard, depth, three segment parameters behind one guard, distances.  Every product / difference is the same
+// IEEE operation the reference performs (EdgeFunctionForward / PointLineDistanceForward), with common
+// subexpressions shared; edge(p,v2,v0) uses -(v2-v0), whose negation commutes with rounding.
+constexpr int kFaceFast = 0x100000;
+
+__device__ __forceinline__ bool eval_pair(const FaceB& r, float xf, float yf, int clip, float blur, unsigned& zbits, float& sd) {
+  if (!(r.flags & kFaceFast)) return eval_pair_generic(r, xf, yf, clip, blur, zbits, sd);
+  const float dx0 = fsub(xf, r.x0), dy0 = fsub(yf, r.y0), dx1 = fsub(xf, r.x1), dy1 = fsub(yf, r.y1);
+  const float dx2 = fsub(xf, r.x2), dy2 = fsub(yf, r.y2);
+  const float ex01 = fsub(r.x1, r.x0), ey01 = fsub(r.y1, r.y0), ex02 = fsub(r.x2, r.x0), ey02 = fsub(r.y2, r.y0);
+  const float ex12 = fsub(r.x2, r.x1), ey12 = fsub(r.y2, r.y1);
+  const float n0 = fsub(fmul(dx1, ey12), fmul(dy1, ex12));  // edge(p,v1,v2)
+  const float n1 = fsub(fmul(dy2, ex02), fmul(dx2, ey02));  // edge(p,v2,v0)
+  const float n2 = fsub(fmul(dx0, ey01), fmul(dy0, ex01));  // edge(p,v0,v1)
+  float w0, w1, w2;
+  if (div_safe3(n0, n1, n2)) {
+    w0 = fdiv_fast(n0, r.den, r.yden); w1 = fdiv_fast(n1, r.den, r.yden); w2 = fdiv_fast(n2, r.den, r.yden);
+  } else {
+    w0 = fdiv_slow(n0, r.den); w1 = fdiv_slow(n1, r.den); w2 = fdiv_slow(n2, r.den);
+  }
+  float c0w = w0, c1w = w1, c2w = w2;
+  if (clip) {
+    c0w = w0 > 0.0f ? w0 : 0.0f; c1w = w1 > 0.0f ? w1 : 0.0f; c2w = w2 > 0.0f ? w2 : 0.0f;
+    float s = fadd(fadd(c0w, c1w), c2w);
+    s = s > 1e-5f ? s : 1e-5f;
+    c0w = fdiv_slow(c0w, s); c1w = fdiv_slow(c1w, s); c2w = fdiv_slow(c2w, s);
+  }
+  float pz = fadd(fadd(fmul(c0w, r.z0), fmul(c1w, r.z1)), fmul(c2w, r.z2));
+  if (pz < 0.0f) return false;
+  const float l01 = fadd(fmul(ex01, ex01), fmul(ey01, ey01));
+  const float l02 = fadd(fmul(ex02, ex02), fmul(ey02, ey02));
+  const float l12 = fadd(fmul(ex12, ex12), fmul(ey12, ey12));
+  const float m01 = fadd(fmul(ex01, dx0), fmul(ey01, dy0));
+  const float m02 = fadd(fmul(ex02, dx0), fmul(ey02, dy0));
+  const float m12 = fadd(fmul(ex12, dx1), fmul(ey12, dy1));
+  float t01, t02, t12;
+  if (div_safe3(m01, m02, m12)) {
+    t01 = fdiv_fast(m01, l01, r.r01); t02 = fdiv_fast(m02, l02, r.r02); t12 = fdiv_fast(m12, l12, r.r12);
+  } else {
+    t01 = fdiv_slow(m01, l01); t02 = fdiv_slow(m02, l02); t12 = fdiv_slow(m12, l12);
+  }
+  const float d01 = seg_dist_t(t01, r.x0, r.y0, ex01, ey01, xf, yf);
+  const float d02 = seg_dist_t(t02, r.x0, r.y0, ex02, ey02, xf, yf);
+  const float d12 = seg_dist_t(t12, r.x1, r.y1, ex12, ey12, xf, yf);
+  const float dist = fminf(fminf(d01, d02), d12);
+  const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
+  if (!inside && dist >= blur) return false;
+  pz = pz + 0.0f;  // canonicalise -0
+  zbits = __float_as_uint(pz);
+  sd = inside ? -dist : dist;
+  return true;
+}
+
+// Full per-face set-up from the three vertices (used once per region face, and by the overflow path).
+struct FaceSetup {
+  FaceB b;
+  float bxmin, bxmax, bymin, bymax;
+  float g[9];  // conservative edge equations (A,B,C) x 3
+};
+
+__device__ __forceinline__ void setup_face(FaceSetup& s, int f, float x0, float y0, float z0, float x1, float y1, float z1,
+                                           float x2, float y2, float z2, float blur, float sq_blur) {
+  FaceB& b = s.b;
+  b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; b.x2 = x2; b.y2 = y2; b.z0 = z0; b.z1 = z1; b.z2 = z2;
+  s.bxmin = fsub(fminf(fminf(x0, x1), x2), sq_blur); s.bxmax = fadd(fmaxf(fmaxf(x0, x1), x2), sq_blur);
+  s.bymin = fsub(fminf(fminf(y0, y1), y2), sq_blur); s.bymax = fadd(fmaxf(fmaxf(y0, y1), y2), sq_blur);
+  b.den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), ACFM_K_EPS);  // bary denominator
+  b.yden = rcp_refined(b.den);
+  const float ex01 = fsub(x1, x0), ey01 = fsub(y1, y0), ex02 = fsub(x2, x0), ey02 = fsub(y2, y0);
+  const float ex12 = fsub(x2, x1), ey12 = fsub(y2, y1);
+  const float l01 = fadd(fmul(ex01, ex01), fmul(ey01, ey01));
+  const float l02 = fadd(fmul(ex02, ex02), fmul(ey02, ey02));
+  const float l12 = fadd(fmul(ex12, ex12), fmul(ey12, ey12));
+  b.r01 = rcp_refined(l01); b.r02 = rcp_refined(l02); b.r12 = rcp_refined(l12);
+  b.flags = f | (div_safe(b.den) ? 0x10000 : 0) | (div_safe(l01) ? 0x20000 : 0) | (div_safe(l02) ? 0x40000 : 0) |
+            (div_safe(l12) ? 0x80000 : 0);
+  if ((b.flags & 0xf0000) == 0xf0000 && l01 > ACFM_K_EPS && l02 > ACFM_K_EPS && l12 > ACFM_K_EPS) b.flags |= kFaceFast;
+  // conservative edge equations (approximate arithmetic; see the header comment)
+  const float mag = fmaxf(fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fabsf(x2)), fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fabsf(y2)));
+  const float T = 1.001f * sq_blur + 1e-5f * (1.0f + mag);
+  const float sgn = b.den > 0.0f ? 1.0f : -1.0f;
+  const bool usable = fabsf(b.den) > 1e-6f && mag < 1e6f;
+  // edge 0: through v1,v2 (n0 = dx1*ey12 - dy1*ex12); edge 1: through v2,v0 (n1 = dy2*ex02 - dx2*ey02);
+  // edge 2: through v0,v1 (n2 = dx0*ey01 - dy0*ex01)
+  const float ea[3] = {ey12, -ey02, ey01}, eb[3] = {-ex12, ex02, -ex01}, el[3] = {l12, l02, l01};
+  const float qx[3] = {x1, x2, x0}, qy[3] = {y1, y2, y0};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float A = 0.0f, B = 0.0f, C = 0.0f;
+    if (usable && el[i] > 1e-12f) {
+      const float inv = sgn / (sqrtf(el[i]) * T);
+      A = ea[i] * inv; B = eb[i] * inv;
+      const float E = 4e-6f * (fabsf(A) * (1.0f + fabsf(qx[i])) + fabsf(B) * (1.0f + fabsf(qy[i])));
+      const float sh = 1.0f / (1.0f + E);
+      A *= sh; B *= sh;
+      C = -(A * qx[i] + B * qy[i]);
+    }
+    s.g[i * 3] = A; s.g[i * 3 + 1] = B; s.g[i * 3 + 2] = C;
+  }
+}
+
+// sorted insertion of (zb, f, sd) into the lane's K-nearest list, ascending (z, face)
+__device__ __forceinline__ void list_insert(unsigned* lz, float* ld, unsigned short* lf, int K, int& cnt, unsigned& lastz,
+                                            unsigned& lastf, unsigned zb, unsigned f, float sd) {
+  int pos;
+  if (cnt < K) {
+    pos = cnt++;
+  } else {
+    if (zb > lastz || (zb == lastz && f > lastf)) return;  // not nearer than the current K-th
+    pos = K - 1;
+  }
+  while (pos > 0) {
+    const unsigned zp = lz[pos - 1];
+    const unsigned fp = lf[pos - 1];
+    if (zp < zb || (zp == zb && fp < f)) break;
+    lz[pos] = zp; lf[pos] = (unsigned short)fp; ld[pos] = ld[pos - 1];
+    --pos;
+  }
+  lz[pos] = zb; lf[pos] = (unsigned short)f; ld[pos] = sd;
+  if (cnt == K) { lastz = lz[K - 1]; lastf = lf[K - 1]; }
+}
+
+template <int NWARPS, typename IdxT>
+__global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterParams p) {
+  constexpr int NT = NWARPS * 32;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const FwdSmem L(p.V, p.F, p.K, NWARPS, p.cap);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  int* rcount = reinterpret_cast<int*>(smem + 8);
+  int* next_tile = reinterpret_cast<int*>(smem + 12);
+  float* red = reinterpret_cast<float*>(smem + L.off_red);
+  int* hist = reinterpret_cast<int*>(smem + L.off_hist);
+  unsigned short* rlist = reinterpret_cast<unsigned short*>(smem + L.off_rlist);
+  float4* recA = reinterpret_cast<float4*>(smem + L.off_recA);  // [4][cap]: bbox | g0 g1.x | g1.yz g2.xy | g2.z
+  float4* recB = reinterpret_cast<float4*>(smem + L.off_recB);  // [4][cap]: x0 y0 x1 y1 | x2 y2 z0 z1 | z2 den yden flags | r01 r02 r12
+  const int cap = p.cap;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int regions = p.regions_x * p.regions_y;
+  const int n = blockIdx.x / regions;
+  const int rg = blockIdx.x - n * regions;
+  const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
+  const int px1 = min(px0 + kRegion, p.W), py1 = min(py0 + kRegion, p.H);
+  const int K = p.K;
+  const long long fbase = (long long)n * p.faces_stride;
+  const float* gverts = p.ndc + (size_t)n * p.V * 3;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    *rcount = 0;
+    *next_tile = 0;
+  }
+  __syncthreads();
+  const float* sv = stage_bulk_1d(smem + L.off_verts, gverts, (uint32_t)p.V * 12u, bar, 0);
+
+  const float r_xhi = pix_to_ndc(p.W - 1 - px0, p.W), r_xlo = pix_to_ndc(p.W - 1 - (px1 - 1), p.W);
+  const float r_yhi = pix_to_ndc(p.H - 1 - py0, p.H), r_ylo = pix_to_ndc(p.H - 1 - (py1 - 1), p.H);
+
+  // ---- 1. mesh bounding box: regions that cannot be touched by any face skip the face scan ----------
+  float zlo = INFINITY, zhi = -INFINITY;
+  {
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    for (int v = tid; v < p.V; v += NT) {
+      const float x = sv[v * 3], y = sv[v * 3 + 1], z = sv[v * 3 + 2];
+      xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+      zlo = fminf(zlo, z); zhi = fmaxf(zhi, z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+      zlo = fminf(zlo, __shfl_xor_sync(0xffffffffu, zlo, o)); zhi = fmaxf(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
+    }
+    if (lane == 0) {
+      red[warp * 8] = xmin; red[warp * 8 + 1] = xmax; red[warp * 8 + 2] = ymin; red[warp * 8 + 3] = ymax;
+      red[warp * 8 + 4] = zlo; red[warp * 8 + 5] = zhi;
+    }
+    if (tid < kZBuckets) hist[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      xmin = fminf(xmin, red[w * 8]); xmax = fmaxf(xmax, red[w * 8 + 1]);
+      ymin = fminf(ymin, red[w * 8 + 2]); ymax = fmaxf(ymax, red[w * 8 + 3]);
+      zlo = fminf(zlo, red[w * 8 + 4]); zhi = fmaxf(zhi, red[w * 8 + 5]);
+    }
+    // same expansion and comparisons as the per-face test below, so this early-out is exact
+    const bool outside = (r_xlo > fadd(xmax, p.sq_blur)) || (r_xhi < fsub(xmin, p.sq_blur)) ||
+                         (r_ylo > fadd(ymax, p.sq_blur)) || (r_yhi < fsub(ymin, p.sq_blur));
+    if (outside) {
+      cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);
+      return;
+    }
+  }
+
+  // ---- 2. cull all faces against the region; bucket the survivors front to back ------------------------
+  // Evaluating near faces first makes the per-pixel K-nearest lists fill with (almost) final entries, so
+  // later candidates are appended or rejected by one compare instead of shifting entries.  The order
+  // inside a bucket (and the order of atomics) is arbitrary: results do not depend on it, only the work.
+  int* tmp = reinterpret_cast<int*>(smem + L.off_tmp);  // (bucket << 16 | face)
+  const float zscale = (zhi > zlo) ? (float)kZBuckets / (3.0f * (zhi - zlo)) : 0.0f;
+  for (int f0 = 0; f0 < p.F; f0 += NT) {
+    const int f = f0 + tid;
+    bool keep = false;
+    int bucket = 0;
+    if (f < p.F) {
+      const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
+      const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
+      const float x0 = sv[i0 * 3], y0 = sv[i0 * 3 + 1], z0 = sv[i0 * 3 + 2];
+      const float x1 = sv[i1 * 3], y1 = sv[i1 * 3 + 1], z1 = sv[i1 * 3 + 2];
+      const float x2 = sv[i2 * 3], y2 = sv[i2 * 3 + 1], z2 = sv[i2 * 3 + 2];
+      const float zmax = fmaxf(fmaxf(z0, z1), z2);
+      const float area = edge_fn(x0, y0, x1, y1, x2, y2);
+      const bool skip = (zmax < 0.0f) || (p.cull && area < 0.0f) || (area <= ACFM_K_EPS && area >= -ACFM_K_EPS);
+      const float bxmin = fsub(fminf(fminf(x0, x1), x2), p.sq_blur), bxmax = fadd(fmaxf(fmaxf(x0, x1), x2), p.sq_blur);
+      const float bymin = fsub(fminf(fminf(y0, y1), y2), p.sq_blur), bymax = fadd(fmaxf(fmaxf(y0, y1), y2), p.sq_blur);
+      keep = !skip && !(r_xlo > bxmax) && !(r_xhi < bxmin) && !(r_ylo > bymax) && !(r_yhi < bymin);
+      bucket = min(kZBuckets - 1, max(0, (int)((z0 + z1 + z2 - 3.0f * zlo) * zscale)));
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(rcount, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+      tmp[base + __popc(m & ((1u << lane) - 1u))] = (bucket << 16) | f;
+      atomicAdd(&hist[bucket], 1);
+    }
+  }
+  __syncthreads();
+  const int nlist = *rcount;
+  if (nlist == 0) {
+    cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);
+    return;
+  }
+  if (warp == 0) {  // exclusive scan of the 64 bucket counts
+    const int a = hist[lane * 2], b = hist[lane * 2 + 1];
+    int incl = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    hist[lane * 2] = incl - a - b;
+    hist[lane * 2 + 1] = incl - b;
+  }
+  __syncthreads();
+  for (int e = tid; e < nlist; e += NT) {
+    const int v = tmp[e];
+    rlist[atomicAdd(&hist[v >> 16], 1)] = (unsigned short)(v & 0xffff);
+  }
+  __syncthreads();
+
+  // ---- 3. per-region face records ------------------------------------------------------------------------
+  const int nrec = min(nlist, cap);
+  for (int j = tid; j < nrec; j += NT) {
+    const int f = rlist[j];
+    const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
+    const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
+    FaceSetup s;
+    setup_face(s, f, sv[i0 * 3], sv[i0 * 3 + 1], sv[i0 * 3 + 2], sv[i1 * 3], sv[i1 * 3 + 1], sv[i1 * 3 + 2], sv[i2 * 3],
+               sv[i2 * 3 + 1], sv[i2 * 3 + 2], p.blur, p.sq_blur);
+    recA[j] = make_float4(s.bxmin, s.bxmax, s.bymin, s.bymax);
+    recA[cap + j] = make_float4(s.g[0], s.g[1], s.g[2], s.g[3]);
+    recA[2 * cap + j] = make_float4(s.g[4], s.g[5], s.g[6], s.g[7]);
+    recA[3 * cap + j] = make_float4(s.g[8], 0.f, 0.f, 0.f);
+    recB[j] = make_float4(s.b.x0, s.b.y0, s.b.x1, s.b.y1);
+    recB[cap + j] = make_float4(s.b.x2, s.b.y2, s.b.z0, s.b.z1);
+    recB[2 * cap + j] = make_float4(s.b.z2, s.b.den, s.b.yden, __int_as_float(s.b.flags));
+    recB[3 * cap + j] = make_float4(s.b.r01, s.b.r02, s.b.r12, 0.f);
+  }
+  __syncthreads();  // the staging scratch (verts, tmp) is dead from here on: the warp slabs alias it
+
+  // ---- 4. warps pull 8x4 tiles; no CTA-wide synchronisation from here on ----------------------------
+  unsigned char* wslab = smem + L.off_union + warp * L.warp_bytes;
+  const int KS = L.KS;
+  unsigned* lz = reinterpret_cast<unsigned*>(wslab + L.w_z) + lane * KS;
+  float* ld = reinterpret_cast<float*>(wslab + L.w_d) + lane * KS;
+  unsigned short* lf = reinterpret_cast<unsigned short*>(wslab + L.w_f) + lane * KS;
+  unsigned char* queue = wslab + L.w_q;     // [slot][lane]
+  unsigned char* cnts = wslab + L.w_cnt;    // [lane]
+  const unsigned* wz = reinterpret_cast<const unsigned*>(wslab + L.w_z);
+  const float* wd = reinterpret_cast<const float*>(wslab + L.w_d);
+  const unsigned short* wf = reinterpret_cast<const unsigned short*>(wslab + L.w_f);
+  const int tiles_x = (px1 - px0 + kTileW - 1) / kTileW, tiles_y = (py1 - py0 + kTileH - 1) / kTileH;
+  const int ntiles = tiles_x * tiles_y;
+  const float inv_sigma_neg = p.sigma > 0.0f ? 1.0f / p.sigma : 0.0f;
+
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(next_tile, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= ntiles) break;
+    const int tx0 = px0 + (t % tiles_x) * kTileW, ty0 = py0 + (t / tiles_x) * kTileH;
+    const int xi = tx0 + (lane & 7), yi = ty0 + (lane >> 3);
+    const bool valid = xi < p.W && yi < p.H;
+    const float xf = pix_to_ndc(p.W - 1 - xi, p.W), yf = pix_to_ndc(p.H - 1 - yi, p.H);
+    const float t_xhi = pix_to_ndc(p.W - 1 - tx0, p.W), t_xlo = pix_to_ndc(p.W - 1 - min(tx0 + kTileW - 1, p.W - 1), p.W);
+    const float t_yhi = pix_to_ndc(p.H - 1 - ty0, p.H), t_ylo = pix_to_ndc(p.H - 1 - min(ty0 + kTileH - 1, p.H - 1), p.H);
+
+    int cnt = 0, qn = 0;
+    unsigned lastz = 0u, lastf = 0u;
+
+    // (c) evaluate: each lane pops its own queue
+    auto drain = [&]() {
+      const int qmax = __reduce_max_sync(0xffffffffu, qn);
+      for (int i = 0; i < qmax; ++i) {
+        if (i < qn) {
+          const int j = queue[i * 32 + lane];
+          const float4 b0 = recB[j], b1 = recB[cap + j], b2 = recB[2 * cap + j], b3 = recB[3 * cap + j];
+          FaceB r;
+          r.x0 = b0.x; r.y0 = b0.y; r.x1 = b0.z; r.y1 = b0.w; r.x2 = b1.x; r.y2 = b1.y; r.z0 = b1.z; r.z1 = b1.w;
+          r.z2 = b2.x; r.den = b2.y; r.yden = b2.z; r.flags = __float_as_int(b2.w);
+          r.r01 = b3.x; r.r02 = b3.y; r.r12 = b3.z;
+          unsigned zb;
+          float sd;
+          if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd)) list_insert(lz, ld, lf, K, cnt, lastz, lastf, zb, r.flags & 0xffff, sd);
+        }
+      }
+      qn = 0;
+    };
+
+    for (int c0 = 0; c0 < nrec; c0 += 32) {
+      // (a) scan: lane = face; tile-level bbox + edge-equation culling
+      const int j = c0 + lane;
+      bool hit = false;
+      if (j < nrec) {
+        const float4 bb = recA[j];
+        hit = !(t_xlo > bb.y) && !(t_xhi < bb.x) && !(t_ylo > bb.w) && !(t_yhi < bb.z);
+        if (hit) {
+          const float4 ga = recA[cap + j], gb = recA[2 * cap + j];
+          const float gc = recA[3 * cap + j].x;
+          const float m0 = fmaf(ga.x, ga.x > 0.f ? t_xhi : t_xlo, fmaf(ga.y, ga.y > 0.f ? t_yhi : t_ylo, ga.z));
+          const float m1 = fmaf(ga.w, ga.w > 0.f ? t_xhi : t_xlo, fmaf(gb.x, gb.x > 0.f ? t_yhi : t_ylo, gb.y));
+          const float m2 = fmaf(gb.z, gb.z > 0.f ? t_xhi : t_xlo, fmaf(gb.w, gb.w > 0.f ? t_yhi : t_ylo, gc));
+          hit = !(m0 < -1.0f) && !(m1 < -1.0f) && !(m2 < -1.0f);
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      // (b) filter: lane = pixel, face uniform; survivors are queued per lane
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int jj = c0 + src;
+        const float4 bb = recA[jj], ga = recA[cap + jj], gb = recA[2 * cap + jj];
+        const float gc = recA[3 * cap + jj].x;
+        bool cand = valid && !(xf > bb.y) && !(xf < bb.x) && !(yf > bb.w) && !(yf < bb.z);
+        const float g0 = fmaf(ga.x, xf, fmaf(ga.y, yf, ga.z));
+        const float g1 = fmaf(ga.w, xf, fmaf(gb.x, yf, gb.y));
+        const float g2 = fmaf(gb.z, xf, fmaf(gb.w, yf, gc));
+        cand = cand && !(g0 < -1.0f) && !(g1 < -1.0f) && !(g2 < -1.0f);
+        if (cand) queue[(qn++) * 32 + lane] = (unsigned char)jj;
+        if (__any_sync(0xffffffffu, qn == kQueue)) drain();
+      }
+    }
+    drain();
+
+    // overflow: region faces without a record (face-uniform evaluation, set-up broadcast by shuffles)
+    for (int c0 = nrec; c0 < nlist; c0 += 32) {
+      const int j = c0 + lane;
+      bool hit = false;
+      FaceSetup s;
+      if (j < nlist) {
+        const int f = rlist[j];
+        const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
+        const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
+        setup_face(s, f, gverts[i0 * 3], gverts[i0 * 3 + 1], gverts[i0 * 3 + 2], gverts[i1 * 3], gverts[i1 * 3 + 1],
+                   gverts[i1 * 3 + 2], gverts[i2 * 3], gverts[i2 * 3 + 1], gverts[i2 * 3 + 2], p.blur, p.sq_blur);
+        hit = !(t_xlo > s.bxmax) && !(t_xhi < s.bxmin) && !(t_ylo > s.bymax) && !(t_yhi < s.bymin);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        FaceB r;
+#define ACFM_BC(field) r.field = __shfl_sync(0xffffffffu, s.b.field, src)
+        ACFM_BC(x0); ACFM_BC(y0); ACFM_BC(x1); ACFM_BC(y1); ACFM_BC(x2); ACFM_BC(y2); ACFM_BC(z0); ACFM_BC(z1); ACFM_BC(z2);
+        ACFM_BC(den); ACFM_BC(yden); ACFM_BC(r01); ACFM_BC(r02); ACFM_BC(r12); ACFM_BC(flags);
+#undef ACFM_BC
+        const float axmin = __shfl_sync(0xffffffffu, s.bxmin, src), axmax = __shfl_sync(0xffffffffu, s.bxmax, src);
+        const float aymin = __shfl_sync(0xffffffffu, s.bymin, src), aymax = __shfl_sync(0xffffffffu, s.bymax, src);
+        if (!valid || xf > axmax || xf < axmin || yf > aymax || yf < aymin) continue;
+        unsigned zb;
+        float sd;
+        if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd)) list_insert(lz, ld, lf, K, cnt, lastz, lastf, zb, r.flags & 0xffff, sd);
+      }
+    }
+
+    // ---- (d) blend, write ------------------------------------------------------------------------------
+    const int npx = min(kTileW, p.W - tx0);
+    const int nrows = min(kTileH, p.H - ty0);
+    const unsigned any = __ballot_sync(0xffffffffu, cnt > 0);
+    if (any == 0u) {
+      for (int row = 0; row < nrows; ++row) {
+        const long long pix = ((long long)n * p.H + ty0 + row) * p.W + tx0;
+        warp_fill_frag(p, pix * K, npx * K, lane);
+      }
+      if (p.mask && valid) p.mask[((long long)n * p.H + yi) * p.W + xi] = 0.0f;
+      continue;
+    }
+    if (p.mask && valid) {
+      float alpha = 1.0f;
+      for (int i = 0; i < cnt; ++i) {
+        const float prob = 1.0f / (1.0f + expf(ld[i] * inv_sigma_neg));
+        alpha *= (1.0f - prob);
+      }
+      p.mask[((long long)n * p.H + yi) * p.W + xi] = 1.0f - alpha;
+    }
+    cnts[lane] = (unsigned char)cnt;
+    __syncwarp();
+    const long long row_stride = (long long)p.W * K;                       // elements between image rows
+    const long long tbase = (((long long)n * p.H + ty0) * p.W + tx0) * K;  // first element of the tile
+    const long long nF = (long long)n * p.F;
+    if (p.vec_ok && (K & 3) == 0) {
+      // p2f: two entries (16 B) per store; zbuf / dists: four entries (16 B) per store
+      const int P2 = K >> 1, P4 = K >> 2;
+      const unsigned d2 = (65536u + (unsigned)P2 - 1u) / (unsigned)P2, d4 = (65536u + (unsigned)P4 - 1u) / (unsigned)P4;
+      for (int e = lane; e < 32 * P2; e += 32) {
+        const int pxl = (int)(((unsigned)e * d2) >> 16);
+        const int k = (e - pxl * P2) * 2;
+        const int col = pxl & 7, row = pxl >> 3;
+        if (col >= npx || row >= nrows) continue;
+        const int c = cnts[pxl];
+        const long long a = k < c ? nF + wf[pxl * KS + k] : -1ll;
+        const long long b = k + 1 < c ? nF + wf[pxl * KS + k + 1] : -1ll;
+        longlong2 v; v.x = a; v.y = b;
+        *reinterpret_cast<longlong2*>(p.p2f + tbase + row * row_stride + col * K + k) = v;
+      }
+      for (int e = lane; e < 32 * P4; e += 32) {
+        const int pxl = (int)(((unsigned)e * d4) >> 16);
+        const int k = (e - pxl * P4) * 4;
+        const int col = pxl & 7, row = pxl >> 3;
+        if (col >= npx || row >= nrows) continue;
+        const int c = cnts[pxl];
+        const int o = pxl * KS + k;
+        float4 z, d;
+        z.x = k < c ? __uint_as_float(wz[o]) : -1.f; d.x = k < c ? wd[o] : -1.f;
+        z.y = k + 1 < c ? __uint_as_float(wz[o + 1]) : -1.f; d.y = k + 1 < c ? wd[o + 1] : -1.f;
+        z.z = k + 2 < c ? __uint_as_float(wz[o + 2]) : -1.f; d.z = k + 2 < c ? wd[o + 2] : -1.f;
+        z.w = k + 3 < c ? __uint_as_float(wz[o + 3]) : -1.f; d.w = k + 3 < c ? wd[o + 3] : -1.f;
+        const long long g = tbase + row * row_stride + col * K + k;
+        *reinterpret_cast<float4*>(p.zbuf + g) = z;
+        *reinterpret_cast<float4*>(p.dists + g) = d;
+      }
+    } else {
+      const unsigned kdiv = (65536u + (unsigned)K - 1u) / (unsigned)K;  // e / K == (e * kdiv) >> 16 for e < 32K <= 2048
+      for (int e = lane; e < 32 * K; e += 32) {
+        const int pxl = (int)(((unsigned)e * kdiv) >> 16);
+        const int k = e - pxl * K;
+        const int col = pxl & 7, row = pxl >> 3;
+        if (col >= npx || row >= nrows) continue;
+        const int c = cnts[pxl];
+        const int o = pxl * KS + k;
+        const long long g = tbase + row * row_stride + col * K + k;
+        p.p2f[g] = k < c ? nF + wf[o] : -1ll;
+        p.zbuf[g] = k < c ? __uint_as_float(wz[o]) : -1.f;
+        p.dists[g] = k < c ? wd[o] : -1.f;
+      }
+    }
+    if (p.bary) {
+      // barycentrics of the surviving fragments are recomputed from the face id with the same operator
+      // sequence as the evaluation above (bit-identical); only the hard (K = 1) texture path asks for them.
+      for (int e = lane; e < 32 * K; e += 32) {
+        const int pxl = e / K;
+        const int k = e - pxl * K;
+        const int col = pxl & 7, row = pxl >> 3;
+        if (col >= npx || row >= nrows) continue;
+        float b0 = -1.f, b1 = -1.f, b2 = -1.f;
+        if (k < cnts[pxl]) {
+          const int fv = wf[pxl * KS + k];
+          const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
+          const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
+          const float x0 = gverts[i0 * 3], y0 = gverts[i0 * 3 + 1], x1 = gverts[i1 * 3], y1 = gverts[i1 * 3 + 1];
+          const float x2 = gverts[i2 * 3], y2 = gverts[i2 * 3 + 1];
+          const float pxf = pix_to_ndc(p.W - 1 - (tx0 + col), p.W), pyf = pix_to_ndc(p.H - 1 - (ty0 + row), p.H);
+          const float den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), ACFM_K_EPS);
+          b0 = fdiv(edge_fn(pxf, pyf, x1, y1, x2, y2), den);
+          b1 = fdiv(edge_fn(pxf, pyf, x2, y2, x0, y0), den);
+          b2 = fdiv(edge_fn(pxf, pyf, x0, y0, x1, y1), den);
+          if (p.clip) {
+            b0 = b0 > 0.0f ? b0 : 0.0f; b1 = b1 > 0.0f ? b1 : 0.0f; b2 = b2 > 0.0f ? b2 : 0.0f;
+            float s = fadd(fadd(b0, b1), b2);
+            s = s > 1e-5f ? s : 1e-5f;
+            b0 = fdiv(b0, s); b1 = fdiv(b1, s); b2 = fdiv(b2, s);
+          }
+        }
+        float* bo = p.bary + (tbase + row * row_stride + col * K + k) * 3;
+        bo[0] = b0; bo[1] = b1; bo[2] = b2;
+      }
+    }
+    __syncwarp();  // the lists are reused by the next tile
+  }
+}
+
+// choose the CTA size and the record capacity: most resident warps per SM (227 KB shared per SM, 1 KB
+// reserved per CTA), then the largest record table that keeps that residency
+int fwd_pick_config(int V, int F, int K, int* smem_bytes, int* cap_out) {
+  int best_nw = 0, best_score = -1, best_cap = 0, best_smem = 0;
+  for (int nw : {8, 10, 12, 4}) {
+    for (int cap : {256, 224, 192, 160, 128, 96, 64}) {
+      const FwdSmem l(V, F, K, nw, cap);
+      if (l.total > 227 * 1024) continue;
+      const int ctas = min(32, (228 * 1024) / (l.total + 1024));
+      const int warps = min(64, ctas * nw);
+      // a record table below ~192 entries overflows on ordinary views (a 32x32 region of the reference
+      // templates sees 130-175 faces, up to ~500), so capacity comes first, then resident warps (capped at 16:
+      // measured on C2, 8-warp CTAs x 2 beat 10 x 2 and 12 x 2), then fewer, larger tables
+      const int score = min(cap, 192) * 10000 + min(warps, 16) * 100 + cap / 32;
+      if (score > best_score) { best_score = score; best_nw = nw; best_cap = cap; best_smem = l.total; }
+    }
+  }
+  *smem_bytes = best_smem;
+  *cap_out = best_cap;
+  return best_nw;
+}
+
+template <int NWARPS, typename IdxT>
+int launch_fwd(const RasterParams& p, int smem, int ctas, cudaStream_t st) {
+  auto kern = raster_fwd_kernel<NWARPS, IdxT>;
+  ACFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<ctas, NWARPS * 32, smem, st>>>(p);
+  ACFM_LAUNCH_OK("raster_fwd_kernel");
+  return ACFM_OK;
+}
+
+// test / tuning hook: ACFM_FWD_WARPS and ACFM_FWD_CAP override the automatic choice
+int fwd_config(int V, int F, int K, int* smem, int* cap) {
+  int nw = fwd_pick_config(V, F, K, smem, cap);
+  const char* ew = getenv("ACFM_FWD_WARPS");
+  const char* ec = getenv("ACFM_FWD_CAP");
+  if (ew || ec) {
+    const int w = ew ? atoi(ew) : nw, c = ec ? atoi(ec) : *cap;
+    if ((w == 4 || w == 8 || w == 10 || w == 12) && c >= 0 && c <= 256) {
+      const FwdSmem l(V, F, K, w, c);
+      if (l.total <= 227 * 1024) { nw = w; *cap = c; *smem = l.total; }
+    }
+  }
+  return nw;
+}
+
+}  // namespace
+
+extern "C" int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes, int* num_ctas,
+                                           int* threads) {
+  ACFM_REQUIRE(N >= 0 && V > 0 && F > 0 && H > 0 && W > 0 && K > 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_launch_info: bad sizes");
+  int smem = 0, cap = 0;
+  const int nw = fwd_config(V, F, K, &smem, &cap);
+  ACFM_REQUIRE(nw > 0, ACFM_ERR_UNSUPPORTED, "rasterizer needs more than 232448 B of shared memory for V=%d F=%d K=%d", V, F, K);
+  if (smem_bytes) *smem_bytes = smem;
+  if (num_ctas) *num_ctas = N * ((W + kRegion - 1) / kRegion) * ((H + kRegion - 1) / kRegion);
+  if (threads) *threads = nw * 32;
+  return ACFM_OK;
+}
+
+extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N,
+                               int V, int F, int H, int W, int K, float blur_radius, int clip_bary, int cull_backfaces,
+                               float sigma, int64_t* pix_to_face, float* zbuf, float* dists, float* bary, float* mask,
+                               void* stream) {
+  ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: bad sizes N=%d V=%d F=%d H=%d W=%d", N, V, F, H, W);
+  ACFM_REQUIRE(K >= 1, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: faces_per_pixel K=%d must be >= 1", K);
+  ACFM_REQUIRE(K <= 64, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: faces_per_pixel K=%d > 64 is not supported", K);
+  ACFM_REQUIRE(blur_radius >= 0.0f, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: blur_radius must be >= 0");
+  ACFM_REQUIRE(!mask || sigma > 0.0f, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: mask output requires sigma > 0");
+  ACFM_REQUIRE(faces_batch_stride == 0 || faces_batch_stride == (int64_t)F * 3, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: faces_batch_stride must be 0 or F*3");
+  if (N == 0) return ACFM_OK;
+  ACFM_REQUIRE(pix_to_face && zbuf && dists, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: null output pointer");
+  ACFM_REQUIRE((ndc || V == 0) && (faces || F == 0), ACFM_ERR_BAD_ARG, "acfm_raster_fwd: null input pointer");
+  ACFM_REQUIRE(F <= 65535 && V <= 65535, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: V=%d, F=%d must be <= 65535", V, F);
+  RasterParams p;
+  p.ndc = ndc; p.faces = faces; p.faces_stride = faces_batch_stride;
+  p.N = N; p.V = V; p.F = F; p.H = H; p.W = W; p.K = K;
+  p.blur = blur_radius; p.sq_blur = sqrtf(blur_radius); p.sigma = sigma;
+  p.clip = clip_bary; p.cull = cull_backfaces;
+  p.p2f = (long long*)pix_to_face; p.zbuf = zbuf; p.dists = dists; p.bary = bary; p.mask = mask;
+  p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
+  p.vec_ok = ((((uintptr_t)pix_to_face) | ((uintptr_t)zbuf) | ((uintptr_t)dists)) & 15u) == 0;
+  int smem = 0, cap = 0;
+  const int nw = fwd_config(V, F, K, &smem, &cap);
+  ACFM_REQUIRE(nw > 0, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: needs more than 232448 B of shared memory for V=%d F=%d K=%d", V, F, K);
+  p.cap = cap;
+  const long long ctas = (long long)N * p.regions_x * p.regions_y;
+  ACFM_REQUIRE(ctas < (1ll << 31), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: too many CTAs");
+  cudaStream_t st = (cudaStream_t)stream;
+#define ACFM_FWD_CASE(NW)                                                                                       \
+  case NW:                                                                                                      \
+    return faces_i64 ? launch_fwd<NW, long long>(p, smem, (int)ctas, st) : launch_fwd<NW, int>(p, smem, (int)ctas, st)
+  switch (nw) {
+    ACFM_FWD_CASE(12);
+    ACFM_FWD_CASE(10);
+    ACFM_FWD_CASE(8);
+    ACFM_FWD_CASE(4);
+  }
+#undef ACFM_FWD_CASE
+  ACFM_REQUIRE(false, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: no launch configuration");
+}

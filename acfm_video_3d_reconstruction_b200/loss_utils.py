@@ -86,12 +86,214 @@ def edt_loss(mask_rendered, edt, reduce=True):
     return _reduce(s[:, 3] / float(mask_rendered[0].numel()), reduce)
 
 
+class _KpLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kp_pred, kp_gt):
+        _lib.require_cuda(kp_pred, kp_gt)
+        kp_pred, kp_gt = F_._f32c(kp_pred), F_._f32c(kp_gt)
+        N, Kp, ps = kp_pred.shape
+        NB = kp_gt.shape[0]
+        if kp_gt.shape[1:] != (Kp, 3) or ps < 2 or (N and (NB == 0 or N % NB)):
+            raise ValueError(f"kp_pred {tuple(kp_pred.shape)} vs kp_gt {tuple(kp_gt.shape)}")
+        loss = torch.empty((N,), dtype=torch.float32, device=kp_pred.device)
+        with torch.cuda.device(kp_pred.device):
+            st = _lib.lib().acfm_kp_loss_fwd(_lib.ptr(kp_pred), ps, _lib.ptr(kp_gt), N, max(NB, 1), Kp, _lib.ptr(loss),
+                                             _lib.stream_of(kp_pred))
+        _lib.check(st, "acfm_kp_loss_fwd")
+        _lib.count()
+        ctx.save_for_backward(kp_pred, kp_gt)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        kp_pred, kp_gt = ctx.saved_tensors
+        N, Kp, ps = kp_pred.shape
+        out = torch.empty_like(kp_pred)
+        with torch.cuda.device(kp_pred.device):
+            st = _lib.lib().acfm_kp_loss_bwd(_lib.ptr(kp_pred), ps, _lib.ptr(kp_gt), _lib.ptr(F_._f32c(g)), N,
+                                             max(kp_gt.shape[0], 1), Kp, _lib.ptr(out), _lib.stream_of(kp_pred))
+        _lib.check(st, "acfm_kp_loss_bwd")
+        _lib.count()
+        return out, None
+
+
 def kp_l2_loss(kp_pred, kp_gt, reduction='mean'):
     """loss_utils.py:341-356 (an L1 over visible keypoints, despite the name).  kp_gt may carry NB <= N rows."""
-    N, NB = kp_pred.shape[0], kp_gt.shape[0]
-    if N != NB:
-        kp_gt = kp_gt.repeat(N // NB, 1, 1)
-    vis = (kp_gt[:, :, 2] > 0).float()
-    loss = (kp_pred - kp_gt[:, :, :2]).abs().sum(-1) * vis
-    loss = loss.mean(-1) / (vis.mean(-1) + 1e-4)
+    loss = _KpLoss.apply(kp_pred, kp_gt)
     return loss.mean() if reduction == 'mean' else loss
+
+
+def visible_vertices(pix_to_face, faces, num_verts):
+    """(N,V) 0/1 floats: vertices of the faces that are nearest at some pixel — the fi_maps/unique/scatter_ block of
+    bds_loss (loss_utils.py:213-223) and optical_flow_loss (:432-441).  pix_to_face (N,H,W,K) int64 packed ids."""
+    _lib.require_cuda(pix_to_face, faces)
+    if pix_to_face.dtype != torch.int64:
+        pix_to_face = pix_to_face.long()
+    pix_to_face = pix_to_face.contiguous()
+    N, H, W, K = pix_to_face.shape
+    fa, i64, fstride, F = F_._faces_arg(faces, N)
+    vis = torch.empty((N, num_verts), dtype=torch.float32, device=pix_to_face.device)
+    with torch.cuda.device(vis.device):
+        st = _lib.lib().acfm_visible_verts(_lib.ptr(pix_to_face), K, _lib.ptr(fa), i64, fstride, N, num_verts, F, H * W,
+                                           _lib.ptr(vis), _lib.stream_of(vis))
+    _lib.check(st, "acfm_visible_verts")
+    _lib.count(2)
+    return vis
+
+
+class _BdsLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, vis, bds, sel):
+        verts, bds = F_._f32c(verts), F_._f32c(bds)
+        N, V, vs = verts.shape
+        NB, P, _ = bds.shape
+        S = sel.numel()
+        loss = torch.empty((N,), dtype=torch.float32, device=verts.device)
+        argmin = torch.empty((N, S), dtype=torch.int32, device=verts.device)
+        with torch.cuda.device(verts.device):
+            st = _lib.lib().acfm_bds_loss_fwd(_lib.ptr(verts), vs, _lib.ptr(vis), _lib.ptr(bds), _lib.ptr(sel), N, max(NB, 1), V,
+                                              P, S, _lib.ptr(loss), _lib.ptr(argmin), _lib.stream_of(verts))
+        _lib.check(st, "acfm_bds_loss_fwd")
+        _lib.count(2)
+        ctx.save_for_backward(verts, bds, sel, argmin)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        verts, bds, sel, argmin = ctx.saved_tensors
+        N, V, vs = verts.shape
+        NB, P, _ = bds.shape
+        gv = torch.empty_like(verts)
+        with torch.cuda.device(verts.device):
+            st = _lib.lib().acfm_bds_loss_bwd(_lib.ptr(verts), vs, _lib.ptr(bds), _lib.ptr(sel), _lib.ptr(argmin),
+                                              _lib.ptr(F_._f32c(g)), N, max(NB, 1), V, P, sel.numel(), _lib.ptr(gv),
+                                              _lib.stream_of(verts))
+        _lib.check(st, "acfm_bds_loss_bwd")
+        _lib.count(2)
+        return gv, None, None, None
+
+
+def bds_loss(verts, bds, faces, pix_to_face, reduce=True, n_samples=1000, k=1):
+    """loss_utils.py:204-237.  verts (N,V,2|3) projected vertices, bds (NB|N,P,3) boundary points [x,y,mask],
+    faces (N,F,3), pix_to_face (N,H,W,K).  Like the reference, up to n_samples boundary points are drawn with
+    torch.randperm from the default (CPU) generator on every call."""
+    if k != 1:
+        raise ValueError("bds_loss: only k=1 (the reference's only call) is implemented")
+    _lib.require_cuda(verts, bds, faces, pix_to_face)
+    indices = torch.randperm(bds.shape[1])[:n_samples]
+    vis = visible_vertices(pix_to_face, faces, verts.shape[1])
+    loss = _BdsLoss.apply(verts, vis, bds, indices.to(verts.device))
+    return loss.mean() if reduce else loss
+
+
+class Boundaries_Loss(torch.nn.Module):
+    """loss_utils.py:240-242"""
+
+    def forward(self, verts, bds, faces, pix_to_face, reduce=True, n_samples=1000):
+        return bds_loss(verts, bds, faces, pix_to_face, reduce=reduce, n_samples=n_samples)
+
+
+class _OfLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, proj, vis, flows, B, T):
+        proj, flows = F_._f32c(proj), F_._f32c(flows)
+        BT, V, ps = proj.shape
+        NBf, H, W = flows.shape[0] // T, flows.shape[1], flows.shape[2]
+        dev = proj.device
+        loss = torch.zeros((B, T - 1), dtype=torch.float32, device=dev)
+        of_pred = torch.empty((B, T - 1, V, 2), dtype=torch.float32, device=dev)
+        samples = torch.empty((B, T - 1, V, 2), dtype=torch.float32, device=dev)
+        vis_out = torch.empty((B, T - 1, V), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.lib().acfm_of_loss_fwd(_lib.ptr(proj), ps, _lib.ptr(vis), _lib.ptr(flows), B, max(NBf, 1), T, V, H, W,
+                                             _lib.ptr(loss), _lib.ptr(of_pred), _lib.ptr(vis_out), _lib.ptr(samples),
+                                             _lib.stream_of(proj))
+        _lib.check(st, "acfm_of_loss_fwd")
+        _lib.count()
+        ctx.save_for_backward(vis_out, of_pred, samples)
+        ctx.cfg = (ps, B, T, V, H, W)
+        ctx.mark_non_differentiable(vis_out, samples)
+        return loss, of_pred, vis_out, samples
+
+    @staticmethod
+    def backward(ctx, g, g_pred, _g2, _g3):
+        vis_out, of_pred, samples = ctx.saved_tensors
+        ps, B, T, V, H, W = ctx.cfg
+        gp = torch.empty((B * T, V, ps), dtype=torch.float32, device=vis_out.device)
+        g = F_._f32c(g) if g is not None else torch.zeros((B, T - 1), dtype=torch.float32, device=vis_out.device)
+        with torch.cuda.device(vis_out.device):
+            st = _lib.lib().acfm_of_loss_bwd(_lib.ptr(vis_out), _lib.ptr(of_pred), _lib.ptr(samples), _lib.ptr(g), ps, B, T, V,
+                                             H, W, _lib.ptr(gp), _lib.stream_of(vis_out))
+        _lib.check(st, "acfm_of_loss_bwd")
+        _lib.count(2)
+        if g_pred is not None:  # of_pred = W/2 * vis * (p_t - p_{t+1}) is also returned; rarely differentiated
+            w = 0.5 * W * vis_out[..., None] * g_pred
+            gp4 = gp.view(B, T, V, ps)
+            gp4[:, :-1, :, :2] += w
+            gp4[:, 1:, :, :2] -= w
+        return gp, None, None, None, None
+
+
+def optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=True):
+    """loss_utils.py:419-474.  meshes (B,T,V,3), faces (B,T,F,3), cams (B*T,7), flows (B|B/G,T,H,W,2);
+    renderer: an OF_NeuralRenderer (its proj_fn projects, its forward gives the K=1 visibility render when
+    pix_to_face is None).  Returns (loss, of_pred, visible_vertices, predicted_points, samples_ofs_gt) as the
+    reference does."""
+    _lib.require_cuda(meshes, faces, cams, flows)
+    b, t, nv, _ = meshes.shape
+    bt = b * t
+    predicted_points = renderer.proj_fn(meshes.reshape(bt, nv, -1), cams.reshape(bt, -1))
+    faces_bt = faces.reshape(bt, faces.shape[2], 3)
+    with torch.no_grad():
+        if pix_to_face is None:
+            pix_to_face = renderer(predicted_points.reshape(bt, nv, 3), faces_bt)
+        else:
+            pix_to_face = pix_to_face[..., :1]
+        vis = visible_vertices(pix_to_face, faces_bt, nv)
+    flows_bt = flows.reshape(-1, flows.shape[2], flows.shape[3], flows.shape[4])
+    loss, of_pred, vis_out, samples = _OfLoss.apply(predicted_points, vis, flows_bt, b, t)
+    if reduce:
+        loss = loss.sum()
+    return loss, of_pred, vis_out, predicted_points[:, :, :2].reshape(b, t, nv, 2), samples
+
+
+class Optical_Flow_Loss(torch.nn.Module):
+    """loss_utils.py:477-479"""
+
+    def forward(self, meshes, faces, cams, flows, renderer, pix_to_face, reduce=True):
+        return optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=reduce)
+
+
+class _HypWeight(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loss):
+        _lib.require_cuda(loss)
+        loss = F_._f32c(loss)
+        G, M = loss.shape
+        probs = torch.empty_like(loss)
+        total = torch.empty((1,), dtype=torch.float32, device=loss.device)
+        with torch.cuda.device(loss.device):
+            st = _lib.lib().acfm_hypothesis_weight_fwd(_lib.ptr(loss), G, M, _lib.ptr(probs), _lib.ptr(total), _lib.stream_of(loss))
+        _lib.check(st, "acfm_hypothesis_weight_fwd")
+        _lib.count(2)
+        ctx.save_for_backward(probs)
+        ctx.mark_non_differentiable(probs)
+        return total[0], probs
+
+    @staticmethod
+    def backward(ctx, g, _gp):
+        probs, = ctx.saved_tensors
+        G, M = probs.shape
+        out = torch.empty_like(probs)
+        g = F_._f32c(g.reshape(1))
+        with torch.cuda.device(probs.device):
+            st = _lib.lib().acfm_hypothesis_weight_bwd(_lib.ptr(probs), _lib.ptr(g), G, M, _lib.ptr(out), _lib.stream_of(probs))
+        _lib.check(st, "acfm_hypothesis_weight_bwd")
+        _lib.count()
+        return out
+
+
+def hypothesis_weighting(total_loss):
+    """total_loss (G, B*T) per hypothesis and frame -> (scalar, probs): probs = softmax(-total_loss, dim=0).detach();
+    scalar = (total_loss * probs).sum(0).mean()  (multiframe/main.py:735-746)."""
+    return _HypWeight.apply(total_loss)

@@ -161,6 +161,63 @@ int acfm_mask_sums_fwd(const float* mask, const float* target, const float* edt,
 int acfm_mask_sums_bwd(const float* mask, const float* target, const float* edt, const float* grad_sums,
                        int N, int NB, int HW, float* grad_mask, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Reprojection losses on the projected mesh (multiframe/nnutils/loss_utils.py; same file in monocular/).
+ * `stride` arguments let the (N,V,3) output of acfm_project_fwd be used in place without slicing out xy.
+ * --------------------------------------------------------------------------------------------- */
+
+/* Visible-vertex bitmap.  Replaces the fi_maps -> faces_[...] -> unique -> scatter_ block of bds_loss
+ * (loss_utils.py:213-223) and optical_flow_loss (:425-441).  pix_to_face: packed ids n*F+f or -1, the nearest
+ * face of pixel i of render n is read at pix_to_face[(n*HW + i) * pix_stride] (pix_stride = K).
+ * vis (N,V) floats 0/1, overwritten. */
+int acfm_visible_verts(const int64_t* pix_to_face, int64_t pix_stride, const void* faces, int faces_i64,
+                       int64_t faces_batch_stride, int N, int V, int F, int HW, float* vis, void* stream);
+
+/* bds_loss (loss_utils.py:204-237), k = 1.  verts (N,V,vert_stride) xy used; vis (N,V); bds (NB,P,3) = [x,y,mask]
+ * read at n % NB; sel (S) int64 indices into P (the caller's randperm(P)[:n_samples]) or NULL for the first S.
+ *   loss[n] = sum_j mask_j * min( 1000 if any vertex is invisible, min_{v visible} |b_j - v|^2 )
+ * argmin (N,S) int32: the minimising vertex or -1 (saved for the backward).  grad_verts (N,V,vert_stride) is
+ * overwritten. */
+int acfm_bds_loss_fwd(const float* verts, int vert_stride, const float* vis, const float* bds, const int64_t* sel, int N,
+                      int NB, int V, int P, int S, float* loss, int* argmin, void* stream);
+int acfm_bds_loss_bwd(const float* verts, int vert_stride, const float* bds, const int64_t* sel, const int* argmin,
+                      const float* grad_loss, int N, int NB, int V, int P, int S, float* grad_verts, void* stream);
+
+/* optical_flow_loss (loss_utils.py:419-474) after the projection and the visibility render.
+ * proj (B*T,V,proj_stride) projected vertices (xy used); vis (B*T,V) visible-vertex bitmap of the K=1 render;
+ * flows (NBf*T,H,W,2) read at sequence b % NBf.  For each sequence b and frame pair (t, t+1):
+ *   gt = flow sampled (nearest, align_corners=False, zero padding) at the projected vertices of frame t+1
+ *   m  = (|gt.x|+|gt.y| != 0) & vis[t+1];  pred = W/2 (p_t - p_{t+1})
+ *   loss[b,t] = sum_v m (|gt.x - pred.x| + |gt.y - pred.y|) / H / (sum_v m + 1)
+ * Outputs loss (B,T-1), of_pred / samples (B,T-1,V,2) (masked), vis_out (B,T-1,V).  grad_proj (B*T,V,proj_stride)
+ * is overwritten. */
+int acfm_of_loss_fwd(const float* proj, int proj_stride, const float* vis, const float* flows, int B, int NBf, int T, int V,
+                     int H, int W, float* loss, float* of_pred, float* vis_out, float* samples, void* stream);
+int acfm_of_loss_bwd(const float* vis_out, const float* of_pred, const float* samples, const float* grad_loss,
+                     int proj_stride, int B, int T, int V, int H, int W, float* grad_proj, void* stream);
+
+/* kp_l2_loss (loss_utils.py:341-356; an L1 over visible keypoints).  kp_pred (N,Kp,pred_stride) xy used; kp_gt (NB,Kp,3)
+ * = [x,y,vis] read at n % NB.  loss[n] = mean_k(vis_k |p-g|_1) / (mean_k vis_k + 1e-4). */
+int acfm_kp_loss_fwd(const float* kp_pred, int pred_stride, const float* kp_gt, int N, int NB, int Kp, float* loss,
+                     void* stream);
+int acfm_kp_loss_bwd(const float* kp_pred, int pred_stride, const float* kp_gt, const float* grad_loss, int N, int NB, int Kp,
+                     float* grad_kp_pred, void* stream);
+
+/* Camera-hypothesis weighting (multiframe/main.py:735-746): loss (G,M) per hypothesis and frame;
+ * probs = softmax(-loss, dim 0), treated as constant; total[0] = mean_m sum_g probs*loss.
+ * Backward: grad_loss = probs * grad_total / M. */
+int acfm_hypothesis_weight_fwd(const float* loss, int G, int M, float* probs, float* total, void* stream);
+int acfm_hypothesis_weight_bwd(const float* probs, const float* grad_total, int G, int M, float* grad_loss, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense mesh Laplacian (V,V).  Replaces geom_utils.mesh_laplacian / laplacian_cot
+ * (multiframe/nnutils/geom_utils.py:159-255,258-325); method 0 = 'uniform' (Meshes.laplacian_packed:
+ * L[i,j] = 1/deg(i), L[i,i] = -1), 1 = 'cot' (L[i,j] = sum cot/4, L[i,i] = -row sum).  No gradient
+ * (the reference builds it under no_grad).
+ * --------------------------------------------------------------------------------------------- */
+int acfm_laplacian_fwd(const float* verts, const void* faces, int faces_i64, int V, int F, int method, float* L,
+                       void* stream);
+
 /* Query: dynamic shared memory (bytes) and CTAs the forward rasterizer launches for a shape
  * (host-only helper used by bench.py for the launch/roofline accounting). */
 int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes,

@@ -2,14 +2,17 @@
 (/root/reference, python) in the authoring container.  /root/reference does not exist on the GPU
 box, so tests only ever read the .npz files written here.
 
-  python tests/golden/make_golden.py
+  python tests/golden/make_golden.py            # everything
+  python tests/golden/make_golden.py reproj      # only the named sections (base | reproj)
 
 What is pinned to the reference's own code:
   templates.npz   verts/faces of the reference's template meshes (monocular/meshes/bird_aligned.obj,
                   multiframe/meshes/horse.obj), parsed from the OBJ text
   projection.npz  nnutils/geom_utils.py: orthographic_proj_withz / orthographic_proj / quat_rotate
-  losses.npz      nnutils/loss_utils.py: l1_loss, iou_loss, edt_loss, kp_l2_loss, bds_loss,
-                  optical_flow_loss (torch CPU, seeded inputs)
+  losses.npz      nnutils/loss_utils.py: l1_loss, iou_loss, edt_loss, kp_l2_loss (torch CPU, seeded inputs)
+  reproj.npz      nnutils/loss_utils.py: bds_loss, optical_flow_loss (values + fp64 gradients), run by the reference's
+                  own code on visibility maps rendered by oracle/; nnutils/geom_utils.py: mesh_laplacian(.., 'cot')
+                  through a duck-typed Meshes; the hypothesis weighting lines of multiframe/main.py:735-746
 What is NOT pinned upstream (PyTorch3D 0.3.0 is not installable: parity unpinned):
   raster_small.npz  fragments / masks / gradients from oracle/ itself — a regression pin of the
                     restated algorithm only.
@@ -53,7 +56,98 @@ def synth_cams(n, gen):
     return torch.cat([s, t, q], 1)
 
 
+class _Meshes:
+    """The three accessors geom_utils.mesh_laplacian / laplacian_cot use on a PyTorch3D Meshes."""
+
+    def __init__(self, v, f):
+        self.v, self.f, self.device = v, f, v.device
+
+    def isempty(self):
+        return False
+
+    def verts_packed(self):
+        return self.v
+
+    def faces_packed(self):
+        return self.f
+
+
+class _RefOFRenderer:
+    """What optical_flow_loss needs from OF_NeuralRenderer: proj_fn (the reference's own) and a K=1 visibility
+    render of already-projected points (oracle/: PyTorch3D itself is not installable)."""
+
+    def __init__(self, img_size):
+        self.img_size = img_size
+        self.proj_fn = ref_geom.orthographic_proj_withz
+
+    def __call__(self, verts, faces):
+        fr = orc.of_renderer(verts.detach().float().numpy(), faces.numpy(), img_size=self.img_size)
+        return torch.from_numpy(fr["pix_to_face"])
+
+
+def reproj(horse_v, horse_f):
+    gen = torch.Generator().manual_seed(7)
+    out = {}
+    # ---- bds_loss: G=2 hypotheses x 2 frames, soft K=20 render for pix_to_face (oracle), boundary points random
+    S, N, NB, P = 64, 4, 2, 300
+    V, F = horse_v.shape[0], horse_f.shape[0]
+    X = torch.from_numpy(horse_v)[None].repeat(N, 1, 1) + 0.02 * torch.randn(N, V, 3, generator=gen)
+    cam = synth_cams(N, gen)
+    faces = torch.from_numpy(horse_f)[None].repeat(N, 1, 1)
+    fr = orc.neural_renderer_mask(X.numpy(), faces.numpy(), cam.numpy(), img_size=S, offset_z=0.0)
+    p2f = torch.from_numpy(fr["pix_to_face"])
+    bds = torch.cat([torch.rand(NB, P, 2, generator=gen) * 1.6 - 0.8, (torch.rand(NB, P, 1, generator=gen) > 0.2).float()], -1)
+    proj = ref_geom.orthographic_proj_withz(X, cam, 0.0)[:, :, :2]
+    torch.manual_seed(123)
+    sel = torch.randperm(P)[:200]
+    torch.manual_seed(123)
+    loss = ref_loss.bds_loss(proj, bds.repeat(N // NB, 1, 1), faces, p2f, reduce=False, n_samples=200)
+    pd = proj.double().requires_grad_(True)
+    torch.manual_seed(123)
+    w = torch.rand(N, generator=gen).double()
+    (ref_loss.bds_loss(pd, bds.repeat(N // NB, 1, 1).double(), faces, p2f, reduce=False, n_samples=200) * w).sum().backward()
+    out.update(bds_X=X.numpy(), bds_cam=cam.numpy(), bds_p2f=fr["pix_to_face"][..., :2].astype(np.int32), bds_proj=proj.numpy(),
+               bds_pts=bds.numpy(), bds_sel=sel.numpy(), bds_loss=loss.numpy(), bds_w=w.numpy(), bds_grad=pd.grad.numpy(), bds_seed=123)
+    # ---- optical_flow_loss: B' = 2 sequences (one flow field shared: the G-fold repeat), T = 3 frames
+    B, T, H = 2, 3, 64
+    M = torch.from_numpy(horse_v)[None, None].repeat(B, T, 1, 1) + 0.03 * torch.randn(B, T, V, 3, generator=gen)
+    cams = synth_cams(B, gen)[:, None].repeat(1, T, 1)
+    cams[:, :, 1:3] += 0.05 * torch.randn(B, T, 2, generator=gen)
+    cams = cams.reshape(B * T, 7)
+    flows = 3.0 * torch.randn(1, T, H, H, 2, generator=gen)
+    flows = flows * (torch.rand(1, T, H, H, 1, generator=gen) > 0.3).float()   # zero flow = "no measurement"
+    faces_of = torch.from_numpy(horse_f)[None, None].repeat(B, T, 1, 1)
+    r = _RefOFRenderer(H)
+    l, of_pred, visv, pts, smp = ref_loss.optical_flow_loss(M, faces_of, cams, flows.repeat(B, 1, 1, 1, 1), r, None, reduce=False)
+    Md = M.double().requires_grad_(True)
+    cd = cams.double().requires_grad_(True)
+    w2 = torch.rand(B, T - 1, generator=gen).double()
+    l64 = ref_loss.optical_flow_loss(Md, faces_of, cd, flows.repeat(B, 1, 1, 1, 1).double(), r, None, reduce=False)[0]
+    (l64 * w2).sum().backward()
+    out.update(of_meshes=M.numpy(), of_cams=cams.numpy(), of_flows=flows.numpy(), of_loss=l.numpy(), of_pred=of_pred.numpy(),
+               of_vis=visv.numpy(), of_pts=pts.numpy(), of_samples=smp.numpy(), of_w=w2.numpy(), of_grad_meshes=Md.grad.numpy(),
+               of_grad_cams=cd.grad.numpy())
+    # ---- cotangent Laplacian of the template (reference code, duck-typed Meshes)
+    hv = torch.from_numpy(horse_v)
+    out["lap_cot"] = ref_geom.mesh_laplacian(_Meshes(hv, torch.from_numpy(horse_f)), "cot").numpy()
+    # ---- hypothesis weighting (multiframe/main.py:735-746)
+    tl = torch.rand(4, 6, generator=gen).double().requires_grad_(True)
+    probs = torch.softmax(-tl, dim=0).detach()
+    tot = (tl * probs).sum(0).mean()
+    tot.backward()
+    out.update(hyp_loss=tl.detach().numpy(), hyp_probs=probs.numpy(), hyp_total=tot.detach().numpy(), hyp_grad=tl.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, "reproj.npz"), **out)
+
+
 def main():
+    sections = set(sys.argv[1:]) or {"base", "reproj"}
+    if "reproj" in sections:
+        t = np.load(os.path.join(HERE, "templates.npz")) if "base" not in sections else None
+        if t is not None:
+            reproj(t["horse_v"], t["horse_f"])
+    if "base" not in sections:
+        print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+        return
     gen = torch.Generator().manual_seed(0)
     bird_v, bird_f = load_obj(os.path.join(REF, "monocular/meshes/bird_aligned.obj"))
     horse_v, horse_f = load_obj(os.path.join(REF, "multiframe/meshes/horse.obj"))
@@ -104,6 +198,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "raster_small.npz"), X=Xr, cam=camr, faces=bird_f, ndc=fr["ndc"],
                         pix_to_face=fr["pix_to_face"].astype(np.int32), zbuf=fr["zbuf"], dists=fr["dists"], mask=fr["mask"],
                         grad_mask=gm, grad_ndc=g_ndc)
+    if "reproj" in sections:
+        reproj(horse_v, horse_f)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

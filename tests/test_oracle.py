@@ -151,3 +151,53 @@ def test_backward_vs_fp64_finite_differences():
             assert abs(fd - g[0, vi, c]) <= 2e-4 * max(1.0, abs(fd)), (vi, c, fd, g[0, vi, c])
             checked += 1
     assert checked >= 8
+
+
+def test_reprojection_losses_restatement_vs_reference_golden():
+    """torch_ref.bds_loss / optical_flow_loss / laplacian_cot / hypothesis_weighting against values and fp64 gradients
+    produced by the reference's own loss_utils / geom_utils / main.py lines (tests/golden/make_golden.py reproj)."""
+    g = util.golden("reproj.npz")
+    _, hf = util.template("horse")
+    hf = torch.from_numpy(hf)
+    # bds_loss
+    N = g["bds_proj"].shape[0]
+    faces = hf[None].repeat(N, 1, 1)
+    bds = torch.from_numpy(g["bds_pts"]).repeat(N // g["bds_pts"].shape[0], 1, 1)
+    p2f = torch.from_numpy(g["bds_p2f"]).long()
+    sel = torch.from_numpy(g["bds_sel"])
+    l = torch_ref.bds_loss(torch.from_numpy(g["bds_proj"]), bds, faces, p2f, sel)
+    assert np.allclose(l.numpy(), g["bds_loss"], rtol=2e-5, atol=0)   # the reference's cdist goes through a matmul
+    pd = torch.from_numpy(g["bds_proj"]).double().requires_grad_(True)
+    (torch_ref.bds_loss(pd, bds.double(), faces, p2f, sel) * torch.from_numpy(g["bds_w"])).sum().backward()
+    assert util.rel_err(pd.grad.numpy(), g["bds_grad"]) < 1e-6
+    # optical_flow_loss: visibility render by the C oracle, as in the golden script
+    M, cams, flows = (torch.from_numpy(g[k]) for k in ("of_meshes", "of_cams", "of_flows"))
+    B, T, V, _ = M.shape
+    faces_of = hf[None, None].repeat(B, T, 1, 1)
+    proj = orc.project(M.reshape(B * T, V, 3).numpy(), cams.numpy(), 0.0)
+    p2f_of = torch.from_numpy(orc.of_renderer(proj, faces_of.reshape(B * T, -1, 3).numpy(), img_size=flows.shape[2])["pix_to_face"])
+    fl = flows.repeat(B, 1, 1, 1, 1)
+    loss, pr, m, gt = torch_ref.optical_flow_loss(M, faces_of, cams, fl, p2f_of)
+    assert np.array_equal(m.numpy(), g["of_vis"]) and m.sum() > 50
+    assert np.allclose(loss.numpy(), g["of_loss"], rtol=1e-5, atol=0)
+    assert np.allclose(pr.numpy(), g["of_pred"], rtol=0, atol=1e-5) and np.array_equal(gt.numpy(), g["of_samples"])
+    Md, cd = M.double().requires_grad_(True), cams.double().requires_grad_(True)
+    (torch_ref.optical_flow_loss(Md, faces_of, cd, fl.double(), p2f_of)[0] * torch.from_numpy(g["of_w"])).sum().backward()
+    assert util.rel_err(Md.grad.numpy(), g["of_grad_meshes"]) < 1e-9
+    assert util.rel_err(cd.grad.numpy(), g["of_grad_cams"]) < 1e-9
+    # cotangent Laplacian, hypothesis weighting
+    hv, _ = util.template("horse")
+    assert util.rel_err(torch_ref.laplacian_cot(torch.from_numpy(hv), hf).numpy(), g["lap_cot"]) < 1e-5
+    tl = torch.from_numpy(g["hyp_loss"]).requires_grad_(True)
+    tot, probs = torch_ref.hypothesis_weighting(tl)
+    tot.backward()
+    assert np.allclose(tot.detach().numpy(), g["hyp_total"]) and np.allclose(probs.numpy(), g["hyp_probs"])
+    assert np.allclose(tl.grad.numpy(), g["hyp_grad"])
+
+
+def test_uniform_laplacian_closed_form():
+    v, f = util.icosphere(1)
+    L = torch_ref.laplacian_uniform(v.shape[0], torch.from_numpy(f))
+    assert torch.allclose(L.sum(1), torch.zeros(v.shape[0]), atol=1e-6)          # rows: -1 + deg * 1/deg
+    assert set(np.unique((L > 0).sum(1).numpy())) <= {5, 6}                         # icosphere vertex degrees
+    assert torch.equal(torch.diagonal(L), -torch.ones(v.shape[0]))
