@@ -138,12 +138,16 @@ class _SoftSilhouette(torch.autograd.Function):
             return None, None, None, None, None, None
         grad_mask = _f32c(grad_mask)
         g = torch.empty_like(ndc)
+        if _lib.event_hook is not None:
+            _lib.event_hook("raster_bwd", 0)
         with torch.cuda.device(ndc.device):
             st = _lib.lib().acfm_raster_soft_bwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma,
                                                  _lib.ptr(p2f), _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(grad_mask),
                                                  _lib.ptr(g), _lib.stream_of(ndc))
         _lib.check(st, "acfm_raster_soft_bwd")
         _lib.count(2)  # memset + kernel
+        if _lib.event_hook is not None:
+            _lib.event_hook("raster_bwd", 1)
         return g, None, None, None, None, None
 
 

@@ -117,6 +117,7 @@ class HotPath:
         self.mean_v = wl.mean_v.to(device)
         self.lbs_param = wl.lbs_param.to(device).requires_grad_(True)
         self.L = wl.L.to(device)
+        self.LtL = self.L.t().matmul(self.L)                       # the Laplacian is fixed at init (monocular/main.py:124)
         self.faces = wl.faces.to(device)[None]                     # shared topology, (1,F,3) int64
         # host-side (pinned) per-step inputs
         self.h_delta = wl.delta.pin_memory()
@@ -153,23 +154,22 @@ class HotPath:
         return sum(t.numel() * t.element_size() for t in (self.h_loss, self.h_gdelta, self.h_gcams))
 
     def step(self, delta, cams, target, edt, world=1):
-        from acfm_video_3d_reconstruction_b200 import deform, loss_utils
+        from acfm_video_3d_reconstruction_b200 import deform, loss_utils, parallel
         from acfm_video_3d_reconstruction_b200 import functional as F_
         cfg = self.cfg
         delta = delta.detach().requires_grad_(True)
         cams = cams.detach().requires_grad_(True)
         self.lbs_param.grad = None
         lbs = torch.softmax(self.lbs_param, dim=0)                 # MeshNet.get_lbs: softmax over vertices
-        W = deform.skinning_matrix(lbs, self.L)
+        W = deform.skinning_matrix(lbs, self.L, self.LtL)
         _, ndc = deform.deform_and_project(self.mean_v, W, delta, cams, offset_z=cfg["offset_z"])
         mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
         ls = loss_utils.mask_losses(mask, target, edt)
         per = (ls["l1"] + W_EDT * ls["edt"]).view(cfg["G"], cfg["frames"])
-        probs = torch.softmax(-per, dim=0).detach()                # hypothesis weighting, multiframe/main.py:735-746
-        total = (per * probs).sum(0).mean()
+        total, _ = loss_utils.hypothesis_weighting(per)            # multiframe/main.py:735-746
         total.backward()
         if world > 1:
-            torch.distributed.all_reduce(self.lbs_param.grad)      # shared-parameter gradient
+            parallel.allreduce_shared_grads([self.lbs_param])      # shared-parameter gradient
         return total.detach(), delta.grad, cams.grad
 
 
@@ -226,6 +226,7 @@ def run_ours(args):
     launches = _lib.launches - launches0
     _lib.event_hook = None
     k_ms = [a[2].elapsed_time(b[2]) for a, b in zip(kev[0::2], kev[1::2]) if a[0] == "raster_fwd"]
+    kb_ms = [a[2].elapsed_time(b[2]) for a, b in zip(kev[0::2], kev[1::2]) if a[0] == "raster_bwd"]
     clk = clocks.stop(t0, t1) if clocks else None
     # ---- timed: end to end (pinned host -> device -> host) ----------------------------------------------------
     for _ in range(2):
@@ -253,6 +254,8 @@ def run_ours(args):
     peak, peak_src = peaks()
     k_avg = float(np.mean(k_ms)) if k_ms else None
     achieved = fwd_b * N_r / (k_avg * 1e-3) / 1e9 if k_avg else None
+    kb_avg = float(np.mean(kb_ms)) if kb_ms else None
+    achieved_b = bwd_b * N_r / (kb_avg * 1e-3) / 1e9 if kb_avg else None
     out = {
         "metric": "render fwd+bwd frames/sec (x camera hyps)", "value": N_r * world * args.steps / (ms * 1e-3),
         "unit": "renders/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -266,12 +269,19 @@ def run_ours(args):
         "roofline": {"kernel": "raster_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": fwd_b * N_r, "avg_launch_ms": k_avg, "launches_timed": len(k_ms)},
+        "roofline_bwd": {"kernel": "raster_soft_bwd_kernel (+ memset of grad_ndc)", "bound": "hbm", "achieved": achieved_b, "peak": peak,
+                         "unit": "GB/s", "frac": achieved_b / peak if achieved_b else None, "traffic": None,
+                         "alg_bytes_per_launch": bwd_b * N_r, "avg_launch_ms": kb_avg, "launches_timed": len(kb_ms),
+                         "note": "algorithmic bytes = reading every fragment (SURVEY.md 8d); the kernel skips the fragment "
+                                 "lists of pixels with mask == 0 or zero upstream gradient, so DRAM traffic is far below them"},
         "clocks": clk,
     }
     traffic = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic):
         try:
-            out["roofline"]["traffic"] = json.load(open(traffic)).get(args.workload, {}).get("raster_fwd_kernel")
+            tj = json.load(open(traffic)).get(args.workload, {})
+            out["roofline"]["traffic"] = tj.get("raster_fwd_kernel")
+            out["roofline_bwd"]["traffic"] = tj.get("raster_soft_bwd_kernel")
         except Exception:
             pass
     if world == 1 and not args.no_cpu_baseline:
