@@ -67,7 +67,7 @@ struct RasterParams {
 // shared-memory carve-up, identical on host and device
 struct FwdSmem {
   int off_red, off_hist, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
-  int w_z, w_d, w_f, w_q, w_cnt;  // offsets inside one warp's slab
+  int w_k, w_d, w_q, w_cnt;  // offsets inside one warp's slab
   int KS;                         // per-lane list stride (odd)
   __host__ __device__ FwdSmem(int V, int F, int K, int nwarps, int cap) {
     int o = 32;  // mbarrier + counters
@@ -82,9 +82,8 @@ struct FwdSmem {
     off_tmp = o + vb;
     KS = K | 1;
     int w = 0;
-    w_z = w; w += KS * 32 * 4;
+    w_k = w; w += KS * 32 * 8;
     w_d = w; w += KS * 32 * 4;
-    w_f = w; w += ((KS * 32 * 2 + 15) / 16) * 16;
     w_q = w; w += kQueue * 32;
     w_cnt = w; w += 32;
     warp_bytes = w;
@@ -273,25 +272,26 @@ __device__ __forceinline__ void setup_face(FaceSetup& s, int f, float x0, float 
   }
 }
 
-// sorted insertion of (zb, f, sd) into the lane's K-nearest list, ascending (z, face)
-__device__ __forceinline__ void list_insert(unsigned* lz, float* ld, unsigned short* lf, int K, int& cnt, unsigned& lastz,
-                                            unsigned& lastf, unsigned zb, unsigned f, float sd) {
+// sorted insertion of key = (depth bits << 32 | face) with payload sd into the lane's K-nearest list, ascending.
+// Depth and face share one 64-bit shared-memory word so that a shift step is LDS.64 + LDS + compare + STS.64 + STS.
+__device__ __forceinline__ void list_insert(unsigned long long* lk, float* ld, int K, int& cnt, unsigned long long& last,
+                                            unsigned long long key, float sd) {
   int pos;
   if (cnt < K) {
     pos = cnt++;
   } else {
-    if (zb > lastz || (zb == lastz && f > lastf)) return;  // not nearer than the current K-th
+    if (key > last) return;  // not nearer than the current K-th
     pos = K - 1;
   }
   while (pos > 0) {
-    const unsigned zp = lz[pos - 1];
-    const unsigned fp = lf[pos - 1];
-    if (zp < zb || (zp == zb && fp < f)) break;
-    lz[pos] = zp; lf[pos] = (unsigned short)fp; ld[pos] = ld[pos - 1];
+    const unsigned long long kp = lk[pos - 1];
+    const float dp = ld[pos - 1];
+    if (kp < key) break;
+    lk[pos] = kp; ld[pos] = dp;
     --pos;
   }
-  lz[pos] = zb; lf[pos] = (unsigned short)f; ld[pos] = sd;
-  if (cnt == K) { lastz = lz[K - 1]; lastf = lf[K - 1]; }
+  lk[pos] = key; ld[pos] = sd;
+  if (cnt == K) last = lk[K - 1];
 }
 
 template <int NWARPS, typename IdxT>
@@ -447,14 +447,12 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
   // ---- 4. warps pull 8x4 tiles; no CTA-wide synchronisation from here on ----------------------------
   unsigned char* wslab = smem + L.off_union + warp * L.warp_bytes;
   const int KS = L.KS;
-  unsigned* lz = reinterpret_cast<unsigned*>(wslab + L.w_z) + lane * KS;
+  unsigned long long* lk = reinterpret_cast<unsigned long long*>(wslab + L.w_k) + lane * KS;
   float* ld = reinterpret_cast<float*>(wslab + L.w_d) + lane * KS;
-  unsigned short* lf = reinterpret_cast<unsigned short*>(wslab + L.w_f) + lane * KS;
   unsigned char* queue = wslab + L.w_q;     // [slot][lane]
   unsigned char* cnts = wslab + L.w_cnt;    // [lane]
-  const unsigned* wz = reinterpret_cast<const unsigned*>(wslab + L.w_z);
+  const uint2* wk = reinterpret_cast<const uint2*>(wslab + L.w_k);  // .x = face, .y = depth bits
   const float* wd = reinterpret_cast<const float*>(wslab + L.w_d);
-  const unsigned short* wf = reinterpret_cast<const unsigned short*>(wslab + L.w_f);
   const int tiles_x = (px1 - px0 + kTileW - 1) / kTileW, tiles_y = (py1 - py0 + kTileH - 1) / kTileH;
   const int ntiles = tiles_x * tiles_y;
   const float inv_sigma_neg = p.sigma > 0.0f ? 1.0f / p.sigma : 0.0f;
@@ -472,7 +470,7 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
     const float t_yhi = pix_to_ndc(p.H - 1 - ty0, p.H), t_ylo = pix_to_ndc(p.H - 1 - min(ty0 + kTileH - 1, p.H - 1), p.H);
 
     int cnt = 0, qn = 0;
-    unsigned lastz = 0u, lastf = 0u;
+    unsigned long long last = 0ull;
 
     // (c) evaluate: each lane pops its own queue
     auto drain = [&]() {
@@ -487,7 +485,8 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
           r.r01 = b3.x; r.r02 = b3.y; r.r12 = b3.z;
           unsigned zb;
           float sd;
-          if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd)) list_insert(lz, ld, lf, K, cnt, lastz, lastf, zb, r.flags & 0xffff, sd);
+          if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd))
+            list_insert(lk, ld, K, cnt, last, ((unsigned long long)zb << 32) | (unsigned)(r.flags & 0xffff), sd);
         }
       }
       qn = 0;
@@ -555,7 +554,8 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
         if (!valid || xf > axmax || xf < axmin || yf > aymax || yf < aymin) continue;
         unsigned zb;
         float sd;
-        if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd)) list_insert(lz, ld, lf, K, cnt, lastz, lastf, zb, r.flags & 0xffff, sd);
+        if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd))
+            list_insert(lk, ld, K, cnt, last, ((unsigned long long)zb << 32) | (unsigned)(r.flags & 0xffff), sd);
       }
     }
 
@@ -594,8 +594,8 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
         const int col = pxl & 7, row = pxl >> 3;
         if (col >= npx || row >= nrows) continue;
         const int c = cnts[pxl];
-        const long long a = k < c ? nF + wf[pxl * KS + k] : -1ll;
-        const long long b = k + 1 < c ? nF + wf[pxl * KS + k + 1] : -1ll;
+        const long long a = k < c ? nF + wk[pxl * KS + k].x : -1ll;
+        const long long b = k + 1 < c ? nF + wk[pxl * KS + k + 1].x : -1ll;
         longlong2 v; v.x = a; v.y = b;
         *reinterpret_cast<longlong2*>(p.p2f + tbase + row * row_stride + col * K + k) = v;
       }
@@ -607,10 +607,10 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
         const int c = cnts[pxl];
         const int o = pxl * KS + k;
         float4 z, d;
-        z.x = k < c ? __uint_as_float(wz[o]) : -1.f; d.x = k < c ? wd[o] : -1.f;
-        z.y = k + 1 < c ? __uint_as_float(wz[o + 1]) : -1.f; d.y = k + 1 < c ? wd[o + 1] : -1.f;
-        z.z = k + 2 < c ? __uint_as_float(wz[o + 2]) : -1.f; d.z = k + 2 < c ? wd[o + 2] : -1.f;
-        z.w = k + 3 < c ? __uint_as_float(wz[o + 3]) : -1.f; d.w = k + 3 < c ? wd[o + 3] : -1.f;
+        z.x = k < c ? __uint_as_float(wk[o].y) : -1.f; d.x = k < c ? wd[o] : -1.f;
+        z.y = k + 1 < c ? __uint_as_float(wk[o + 1].y) : -1.f; d.y = k + 1 < c ? wd[o + 1] : -1.f;
+        z.z = k + 2 < c ? __uint_as_float(wk[o + 2].y) : -1.f; d.z = k + 2 < c ? wd[o + 2] : -1.f;
+        z.w = k + 3 < c ? __uint_as_float(wk[o + 3].y) : -1.f; d.w = k + 3 < c ? wd[o + 3] : -1.f;
         const long long g = tbase + row * row_stride + col * K + k;
         *reinterpret_cast<float4*>(p.zbuf + g) = z;
         *reinterpret_cast<float4*>(p.dists + g) = d;
@@ -625,8 +625,8 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
         const int c = cnts[pxl];
         const int o = pxl * KS + k;
         const long long g = tbase + row * row_stride + col * K + k;
-        p.p2f[g] = k < c ? nF + wf[o] : -1ll;
-        p.zbuf[g] = k < c ? __uint_as_float(wz[o]) : -1.f;
+        p.p2f[g] = k < c ? nF + wk[o].x : -1ll;
+        p.zbuf[g] = k < c ? __uint_as_float(wk[o].y) : -1.f;
         p.dists[g] = k < c ? wd[o] : -1.f;
       }
     }
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
         if (col >= npx || row >= nrows) continue;
         float b0 = -1.f, b1 = -1.f, b2 = -1.f;
         if (k < cnts[pxl]) {
-          const int fv = wf[pxl * KS + k];
+          const int fv = (int)wk[pxl * KS + k].x;
           const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
           const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
           const float x0 = gverts[i0 * 3], y0 = gverts[i0 * 3 + 1], x1 = gverts[i1 * 3], y1 = gverts[i1 * 3 + 1];
