@@ -285,7 +285,7 @@ def run_ours(args):
         except Exception:
             pass
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(cfg, hp.wl, max_seconds=20.0)
+        out["cpu_baseline"] = cpu_baseline(cfg, hp.wl, hp.h_target, hp.h_edt, max_seconds=20.0)
     print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -294,31 +294,73 @@ def run_ours(args):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arms (the oracle as checker-turned-baseline: the only place bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------------------------------
-def _oracle_step(wl, cfg, idx, threads):
-    """fwd (project, view, naive raster, blend) + bwd (blend, raster, scatter) of `idx` renders on the host."""
+def _cpu_targets(wl, cfg, frames, threads):
+    """mask_gt / edt of the sampled frames for the CPU arm (set-up, untimed): an oracle render of an independently drawn pose."""
+    from scipy.ndimage import distance_transform_edt
+    from acfm_video_3d_reconstruction_b200 import synthetic
     from oracle import pt3d_oracle as orc
-    X = wl.mean_v.numpy()[None].repeat(len(idx), 0)
-    cams = wl.cams.numpy()[idx]
-    faces = wl.faces.numpy()[None].repeat(len(idx), 0)
-    fr = orc.neural_renderer_mask(X, faces, cams, img_size=cfg["img"], offset_z=cfg["offset_z"], K=cfg["K"], threads=threads)
-    gm = np.sign(fr["mask"] - 0.5).astype(np.float32) / fr["mask"][0].size
-    orc.neural_renderer_mask_backward(fr, faces, gm)
+    cams = synthetic.cameras(cfg["frames"], 1, seed=1000).numpy()[frames]
+    X = wl.mean_v.numpy()[None].repeat(len(frames), 0)
+    faces = wl.faces.numpy()[None].repeat(len(frames), 0)
+    m = orc.neural_renderer_mask(X, faces, cams, img_size=cfg["img"], offset_z=cfg["offset_z"], K=cfg["K"], threads=threads)["mask"]
+    tgt = (m > 0.5).astype(np.float32)
+    edt = np.stack([distance_transform_edt(1 - t) for t in tgt]).astype(np.float32)
+    return torch.from_numpy(tgt), torch.from_numpy(edt)
 
 
-def cpu_baseline(cfg, wl, max_seconds=20.0):
+def _oracle_step(wl, cfg, frames, threads, target, edt):
+    """The reference's CPU implementation of one hot-path step over `frames` (all G hypotheses of each): the reference's
+    own deformation block (multiframe/main.py:586-609: per-frame batched Cholesky, torch CPU), projection, the restated
+    PyTorch3D 0.3.0 naive CPU rasterizer + blend (oracle/, OpenMP), mask losses, hypothesis weighting, and the backward of
+    all of it down to the handle offsets, cameras and handle weights."""
+    from oracle import pt3d_oracle as orc
+    from oracle import torch_ref
+    G, nb, FT = cfg["G"], len(frames), cfg["frames"]
+    lbs_param = wl.lbs_param.clone().requires_grad_(True)
+    delta = wl.delta[frames].clone().requires_grad_(True)
+    rows = torch.cat([g * FT + torch.as_tensor(frames) for g in range(G)])
+    cams = wl.cams[rows].clone().requires_grad_(True)
+    # ---- deformation exactly as the reference batches it (B*T identical V x V systems) ----
+    lbs = torch.softmax(lbs_param, dim=0).t()[None].repeat(nb, 1, 1)          # (nb,Kh,V)
+    mean = wl.mean_v[None].repeat(nb, 1, 1)
+    delta_v = lbs.bmm(mean) + delta
+    Lb = wl.L[None].repeat(nb, 1, 1)
+    A_augm = Lb.permute(0, 2, 1).matmul(Lb) + lbs.permute(0, 2, 1).matmul(lbs)
+    rhs = Lb.permute(0, 2, 1) @ torch.bmm(Lb, mean) + lbs.permute(0, 2, 1) @ delta_v
+    pred_v = torch.cholesky_solve(rhs, torch.linalg.cholesky(A_augm))
+    # ---- render (C oracle) ----
+    ndc_t = torch_ref.to_ndc(pred_v.repeat(G, 1, 1), cams, cfg["offset_z"])
+    faces = wl.faces.numpy()[None].repeat(G * nb, 0)
+    fr = orc.rasterize(ndc_t.detach().numpy(), faces, cfg["img"], orc.BLUR_SOFT, cfg["K"], threads=threads, want_bary=False)
+    fr["ndc"] = ndc_t.detach().numpy()
+    mask = torch.from_numpy(orc.sigmoid_alpha_blend(fr["dists"], fr["pix_to_face"])).requires_grad_(True)
+    # ---- losses + hypothesis weighting (torch CPU) ----
+    per = (torch_ref.l1_loss(mask, target.repeat(G, 1, 1)) + W_EDT * torch_ref.edt_loss(mask, edt.repeat(G, 1, 1)[:, None])).view(G, nb)
+    total, _ = torch_ref.hypothesis_weighting(per)
+    total.backward()
+    # ---- backward: blend + rasterizer (C oracle), then projection / deformation (torch autograd) ----
+    g_ndc = orc.neural_renderer_mask_backward(fr, faces, mask.grad.numpy())
+    ndc_t.backward(torch.from_numpy(g_ndc))
+    return float(total), delta.grad, cams.grad, lbs_param.grad
+
+
+def cpu_baseline(cfg, wl, target, edt, max_seconds=20.0):
     from oracle import pt3d_oracle as orc
     threads = orc.max_threads()
-    n = max(4, min(wl.cams.shape[0], 2 * threads))
+    torch.set_num_threads(threads)
+    G = cfg["G"]
     t = time.time()
-    _oracle_step(wl, cfg, list(range(2)), threads)  # page-in / thread pool warm-up + cost estimate
-    est = (time.time() - t) / 2
-    n = int(max(2, min(n, max_seconds / max(est, 1e-6))))
+    _oracle_step(wl, cfg, [0], threads, target[:1], edt[:1])  # page-in / thread pool warm-up + cost estimate
+    est = time.time() - t
+    nf = int(max(1, min(cfg["frames"], max_seconds / max(est, 1e-6))))
+    frames = list(range(nf))
     t = time.time()
-    _oracle_step(wl, cfg, list(range(n)), threads)
+    _oracle_step(wl, cfg, frames, threads, target[:nf], edt[:nf])
     dt = time.time() - t
-    return {"value": n / dt, "unit": "renders/s", "cores": threads, "kind": "port",
-            "sample": f"{n} renders of the same workload (project + naive O(pixels x faces) raster + blend, fwd+bwd), "
-                      f"oracle/ restatement of PyTorch3D 0.3.0's CPU path, OpenMP over (render,row), {dt:.1f} s"}
+    return {"value": nf * G / dt, "unit": "renders/s", "cores": threads, "kind": "port",
+            "sample": f"{nf} frames x {G} hypotheses = {nf * G} renders of the same workload: reference deformation block (batched "
+                      f"Cholesky, torch CPU) + oracle/ restatement of PyTorch3D 0.3.0's naive CPU rasterizer (OpenMP over render,row) "
+                      f"+ blend + mask losses + hypothesis weighting, fwd+bwd, {dt:.1f} s"}
 
 
 def run_reference(args):
@@ -331,17 +373,22 @@ def run_reference(args):
     cfg = WORKLOADS[args.workload]
     wl = synthetic.Workload(cfg["template"], cfg["frames"], cfg["G"], cfg["handles"], cfg["img"], seed=0, offset_z=cfg["offset_z"])
     threads = orc.max_threads()
-    n = max(2, min(threads, 16))
-    idx = list(range(n))
+    torch.set_num_threads(threads)
+    G = cfg["G"]
+    nf = max(1, min(cfg["frames"], max(1, threads // G) if cfg["img"] <= 256 else 1))
+    frames = list(range(nf))
+    target, edt = _cpu_targets(wl, cfg, frames, threads)
     for _ in range(args.warmup):
-        _oracle_step(wl, cfg, idx[:2], threads)
+        _oracle_step(wl, cfg, frames[:1], threads, target[:1], edt[:1])
     t = time.time()
     for _ in range(args.steps):
-        _oracle_step(wl, cfg, idx, threads)
+        _oracle_step(wl, cfg, frames, threads, target, edt)
     dt = time.time() - t
+    n = nf * G
     val = n * args.steps / dt
-    sample = (f"each step = {n} of the workload's {wl.renders} renders/GPU (bounded sample), restated PyTorch3D 0.3.0 CPU "
-              f"algorithm (oracle/), OpenMP {threads} threads; the real PyTorch3D wheel is not installable offline")
+    sample = (f"each step = {nf} frames x {G} hypotheses = {n} of the workload's {wl.renders} renders/GPU (bounded sample): reference "
+              f"deformation block (torch CPU) + restated PyTorch3D 0.3.0 CPU rasterizer (oracle/, OpenMP {threads} threads) + losses, "
+              f"fwd+bwd; the real PyTorch3D wheel is not installable offline")
     print(json.dumps({
         "impl": "reference", "metric": "render fwd+bwd frames/sec (x camera hyps)", "value": val, "unit": "renders/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,

@@ -169,3 +169,35 @@ def test_backward_vs_oracle():
     (torch_ref.to_ndc(Xd, cd, 5.0) * torch.from_numpy(g_ndc_ref).double()).sum().backward()
     assert util.rel_err(Xc.grad.cpu().numpy(), Xd.grad.numpy()) < 1e-3
     assert util.rel_err(cc.grad.cpu().numpy(), cd.grad.numpy()) < 1e-3
+
+
+def test_many_random_poses_partly_off_screen():
+    """24 views with scales 0.15-1.3 and translations up to +-0.7 (partly off screen, tiny and huge on screen): exercises the
+    conservative edge/bbox culling at every scale and the record-overflow path (tiny meshes put all faces in one region)."""
+    v, f = util.template("horse")
+    N, S = 24, 96
+    gen = torch.Generator().manual_seed(77)
+    cam = util.synth_cams(N, seed=5)
+    cam[:, 0] = (torch.rand(N, generator=gen) * 1.15 + 0.15).numpy()
+    cam[:, 1:3] = (torch.rand(N, 2, generator=gen) * 1.4 - 0.7).numpy()
+    X = util.synth_verts(v, N, seed=9)
+    faces = np.repeat(f[None], N, 0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=0.0)
+    out = _gpu_mask_render(X, faces, cam, S, 0.0)
+    _assert_fragments_equal(out, ref)
+    assert (ref["pix_to_face"][..., -1] >= 0).any(axis=(1, 2)).sum() >= N // 2
+
+
+@pytest.mark.parametrize("cap,warps", [(64, 8), (96, 4), (256, 12)])
+def test_record_capacity_and_cta_shapes(cap, warps, monkeypatch):
+    """Forcing a small record table sends most region faces through the overflow (face-uniform) path; 4- and 12-warp CTAs
+    are the shapes picked for large K / large meshes.  Results must not depend on either."""
+    monkeypatch.setenv("ACFM_FWD_CAP", str(cap))
+    monkeypatch.setenv("ACFM_FWD_WARPS", str(warps))
+    v, f = util.template("bird")
+    N, S = 3, 128
+    X, cam = util.synth_verts(v, N, seed=31), util.synth_cams(N, seed=32)
+    faces = np.repeat(f[None], N, 0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
+    out = _gpu_mask_render(X, faces, cam, S, 5.0)
+    _assert_fragments_equal(out, ref)

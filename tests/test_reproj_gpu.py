@@ -97,7 +97,7 @@ def test_kp_loss_vs_reference_golden():
     kp_gt = torch.from_numpy(g["kp_gt"]).cuda()
     l = loss_utils.kp_l2_loss(kp_pred, kp_gt, reduction="none")
     assert np.allclose(l.detach().cpu().numpy(), g["kp"], rtol=1e-6, atol=0)
-    assert np.allclose(float(loss_utils.kp_l2_loss(kp_pred, kp_gt)), g["kp_mean"], rtol=1e-6)
+    assert np.allclose(float(loss_utils.kp_l2_loss(kp_pred, kp_gt).detach()), g["kp_mean"], rtol=1e-6)
     w = torch.rand(kp_pred.shape[0], device="cuda")
     (l * w).sum().backward()
     pd = torch.from_numpy(g["kp_pred"]).double().requires_grad_(True)
