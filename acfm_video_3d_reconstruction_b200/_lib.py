@@ -50,6 +50,9 @@ SIGNATURES = {
     "acfm_hypothesis_weight_fwd": [_c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
     "acfm_hypothesis_weight_bwd": [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_laplacian_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_edt_fwd": [_c_vp, _c_int, _c_int, _c_int, _c_f, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
+    "acfm_boundaries_count": [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
+    "acfm_boundaries_write": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_raster_fwd_launch_info": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],
 }
 

@@ -284,11 +284,50 @@ def run_ours(args):
             out["roofline_bwd"]["traffic"] = tj.get("raster_soft_bwd_kernel")
         except Exception:
             pass
+    if world == 1:
+        out["target_maps"] = target_maps_bench(hp, cfg, peak, cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(cfg, hp.wl, hp.h_target, hp.h_edt, max_seconds=20.0)
     print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def target_maps_bench(hp, cfg, peak, cpu=True, iters=10):
+    """Side measurement (not part of `value`): the per-step target maps of set_input for this
+    rank's frames — compute_dt(norm=False) + compute_dt_barrier + compute_boundaries — on the GPU vs the reference's
+    CPU route (scipy EDT twice per mask + find_boundaries, serial in the main thread) on a bounded sample."""
+    from acfm_video_3d_reconstruction_b200 import image_utils
+    m = hp.h_target.to(hp.device)
+    nb, H, W = m.shape
+    for _ in range(3):
+        image_utils.compute_dt_both(m)
+        image_utils.compute_boundaries(m)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        image_utils.compute_dt_both(m)
+        bd = image_utils.compute_boundaries(m)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = nb * (H * W * (4 + 4 + 4) + bd.shape[1] * 12)          # mask in, edt + barrier out, boundary list out
+    out = {"value": nb / (ms * 1e-3), "unit": "masks/s", "masks": nb, "size": [H, W], "ms": ms,
+           "alg_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak,
+           "note": "includes the one host sync compute_boundaries needs for its data-dependent length"}
+    if cpu:
+        from oracle import targets_ref as tr
+        mn = hp.h_target[:8].numpy()
+        t = time.time()
+        for x in mn:
+            tr.compute_dt(x, norm=False)
+            tr.compute_dt_barrier(x)
+        tr.compute_boundaries(mn)
+        dt = time.time() - t
+        out["cpu_baseline"] = {"value": len(mn) / dt, "unit": "masks/s", "cores": 1, "kind": "port",
+                               "sample": f"{len(mn)} masks, scipy.ndimage EDT x3 + restated find_boundaries, serial as in set_input"}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -218,6 +218,27 @@ int acfm_hypothesis_weight_bwd(const float* probs, const float* grad_total, int 
 int acfm_laplacian_fwd(const float* verts, const void* faces, int faces_i64, int V, int F, int method, float* L,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Target maps from the ground-truth masks.  Replaces utils/image.py compute_dt /
+ * compute_dt_barrier / compute_boundaries (multiframe/utils/image.py:94-146), run on the CPU per mask per step by
+ * ShapeTrainer.set_input (multiframe/main.py:364-377).  masks (NB,H,W) floats.
+ *   edt_out[n]     = distance_transform_edt(1 - mask)  [/ max(H,W) if norm]            (compute_dt)
+ *   barrier_out[n] = 1 / (1 + exp(-k * (edt(1 - mask) - edt(mask)) / max(H,W)))        (compute_dt_barrier, k = 50)
+ * Exact (integer squared distances, fp64 square root rounded to fp32).  Either output may be NULL.
+ * workspace: 2*NB*H*W int32, caller-owned.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_edt_fwd(const float* masks, int NB, int H, int W, float k, int norm, float* edt_out, float* barrier_out,
+                 int* workspace, void* stream);
+
+/* compute_boundaries in two steps (the output length depends on the data): acfm_boundaries_count fills
+ * row_offsets (NB,H) (exclusive prefix of the per-row boundary-pixel counts) and totals (NB); the caller reads max(totals)
+ * and allocates out (NB,max_bd,3); acfm_boundaries_write fills [x, y, 1] per boundary pixel in row-major order,
+ * x = (col/W - 0.5)*2, y = (row/H - 0.5)*2, and pads with (-1,-1,0) like the reference.  Boundary =
+ * skimage.segmentation.find_boundaries(mode='thick', connectivity=1): the pixel and its 4 neighbours are not all equal. */
+int acfm_boundaries_count(const float* masks, int NB, int H, int W, int* row_offsets, int* totals, void* stream);
+int acfm_boundaries_write(const float* masks, const int* row_offsets, const int* totals, int NB, int H, int W, int max_bd,
+                          float* out, void* stream);
+
 /* Query: dynamic shared memory (bytes) and CTAs the forward rasterizer launches for a shape
  * (host-only helper used by bench.py for the launch/roofline accounting). */
 int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes,

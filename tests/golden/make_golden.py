@@ -3,7 +3,7 @@
 box, so tests only ever read the .npz files written here.
 
   python tests/golden/make_golden.py            # everything
-  python tests/golden/make_golden.py reproj      # only the named sections (base | reproj)
+  python tests/golden/make_golden.py reproj      # only the named sections (base | reproj | targets)
 
 What is pinned to the reference's own code:
   templates.npz   verts/faces of the reference's template meshes (monocular/meshes/bird_aligned.obj,
@@ -13,6 +13,9 @@ What is pinned to the reference's own code:
   reproj.npz      nnutils/loss_utils.py: bds_loss, optical_flow_loss (values + fp64 gradients), run by the reference's
                   own code on visibility maps rendered by oracle/; nnutils/geom_utils.py: mesh_laplacian(.., 'cot')
                   through a duck-typed Meshes; the hypothesis weighting lines of multiframe/main.py:735-746
+  targets.npz     utils/image.py: compute_dt, compute_dt_barrier, compute_boundaries run by the reference's own code
+                  (scipy present; cv2 stubbed — unused on this path; skimage absent: find_boundaries is restated from its
+                  published implementation, grey_dilation != grey_erosion over the connectivity-1 footprint)
 What is NOT pinned upstream (PyTorch3D 0.3.0 is not installable: parity unpinned):
   raster_small.npz  fragments / masks / gradients from oracle/ itself — a regression pin of the
                     restated algorithm only.
@@ -139,8 +142,54 @@ def reproj(horse_v, horse_f):
     np.savez_compressed(os.path.join(HERE, "reproj.npz"), **out)
 
 
+def targets():
+    import scipy.ndimage as ndi
+    sys.modules.setdefault("cv2", types.ModuleType("cv2"))
+    sk, seg = types.ModuleType("skimage"), types.ModuleType("skimage.segmentation")
+
+    def find_boundaries(label_img, connectivity=1, mode="thick", background=0):
+        """skimage.segmentation.find_boundaries, mode='thick' (skimage/segmentation/boundaries.py)."""
+        if label_img.dtype == "bool":
+            label_img = label_img.astype(np.uint8)
+        fp = ndi.generate_binary_structure(label_img.ndim, connectivity)
+        return ndi.grey_dilation(label_img, footprint=fp) != ndi.grey_erosion(label_img, footprint=fp)
+
+    seg.find_boundaries = find_boundaries
+    sk.segmentation = seg
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.segmentation", seg)
+    sys.path.insert(0, os.path.join(REF, "multiframe"))
+    from utils import image as ref_image
+    t = np.load(os.path.join(HERE, "templates.npz"))
+    gen = torch.Generator().manual_seed(11)
+    N, S = 3, 64
+    X = torch.from_numpy(t["horse_v"])[None].repeat(N, 1, 1).numpy()
+    cam = synth_cams(N, gen).numpy()
+    faces = np.repeat(t["horse_f"][None], N, 0)
+    m = (orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=0.0)["mask"] > 0.5).astype(np.float32)
+    m[0, 20:24, 30:34] = 0          # a hole
+    m[1, 0, :] = 1                  # touches the border
+    out = {"masks": m}
+    out["dt_raw"] = np.stack([ref_image.compute_dt(x, norm=False) for x in m])
+    out["dt_norm"] = np.stack([ref_image.compute_dt(x) for x in m])
+    out["barrier"] = np.stack([ref_image.compute_dt_barrier(x) for x in m])
+    out["boundaries"] = ref_image.compute_boundaries(m)
+    # non-square, non-power-of-two map; an empty and a full mask (scipy's degenerate-input behaviour)
+    r = (torch.rand(3, 40, 72, generator=gen) > 0.97).float().numpy()
+    r[1] = 0
+    r[2] = 1
+    out["masks_b"] = r
+    out["dt_raw_b"] = np.stack([ref_image.compute_dt(x, norm=False) for x in r])
+    out["dt_norm_b"] = np.stack([ref_image.compute_dt(x) for x in r])
+    out["barrier_b"] = np.stack([ref_image.compute_dt_barrier(x, k=20) for x in r])
+    out["boundaries_b"] = ref_image.compute_boundaries(r)
+    np.savez_compressed(os.path.join(HERE, "targets.npz"), **out)
+
+
 def main():
-    sections = set(sys.argv[1:]) or {"base", "reproj"}
+    sections = set(sys.argv[1:]) or {"base", "reproj", "targets"}
+    if "targets" in sections:
+        targets()
     if "reproj" in sections:
         t = np.load(os.path.join(HERE, "templates.npz")) if "base" not in sections else None
         if t is not None:

@@ -201,3 +201,21 @@ def test_uniform_laplacian_closed_form():
     assert torch.allclose(L.sum(1), torch.zeros(v.shape[0]), atol=1e-6)          # rows: -1 + deg * 1/deg
     assert set(np.unique((L > 0).sum(1).numpy())) <= {5, 6}                         # icosphere vertex degrees
     assert torch.equal(torch.diagonal(L), -torch.ones(v.shape[0]))
+
+
+def test_target_maps_restatement_vs_reference_golden():
+    """oracle/targets_ref.py against utils/image.py outputs (tests/golden/make_golden.py targets); the EDT additionally
+    against exhaustive search, and the fp64-sqrt-then-fp32 rounding the CUDA kernel relies on against correctly rounded
+    fp32 square roots of every squared distance a 1024^2 map can produce."""
+    from oracle import targets_ref as tr
+    g = util.golden("targets.npz")
+    for sfx, k in (("", 50), ("_b", 20)):
+        m = g["masks" + sfx]
+        assert np.array_equal(np.stack([tr.compute_dt(x, norm=False) for x in m]), g["dt_raw" + sfx])
+        assert np.array_equal(np.stack([tr.compute_dt(x) for x in m]), g["dt_norm" + sfx])
+        assert np.array_equal(np.stack([tr.compute_dt_barrier(x, k=k) for x in m]), g["barrier" + sfx])
+        assert np.array_equal(tr.compute_boundaries(m), g["boundaries" + sfx])
+    m = g["masks"][0]
+    assert np.array_equal(tr.edt_bruteforce(m == 1), np.rint(g["dt_raw"][0] ** 2).astype(np.int64))
+    n = np.arange(0, 2 * 1024 * 1024 + 1, dtype=np.float64)
+    assert np.array_equal(np.sqrt(n).astype(np.float32), np.sqrt(n.astype(np.float32)))
