@@ -41,6 +41,23 @@ void acfm_set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
+// Raise a kernel's dynamic shared-memory limit once per (kernel instantiation, device, size): keeps
+// cudaFuncSetAttribute out of the steady-state launch path (host time; and nothing but launches inside a CUDA-graph
+// capture).  `slot` is a per-instantiation static array, one entry per device.
+#include <atomic>
+constexpr int kAcfmMaxDevices = 64;
+template <typename Kern>
+inline cudaError_t acfm_ensure_smem(Kern kern, int bytes, std::atomic<int>* slot) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::atomic<int>& cur = slot[dev & (kAcfmMaxDevices - 1)];
+  if (bytes <= cur.load(std::memory_order_acquire)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) cur.store(bytes, std::memory_order_release);
+  return e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // strict IEEE fp32: one rounding per operator, never contracted into FMA.  The rasterizer and
 // the projection reproduce the reference's CPU operator order bit for bit.

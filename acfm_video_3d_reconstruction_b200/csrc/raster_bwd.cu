@@ -198,7 +198,8 @@ int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* fa
   ACFM_REQUIRE(ctas < (1ll << 31), ACFM_ERR_UNSUPPORTED, "%s: too many CTAs", who);
 #define ACFM_LAUNCH_BWD(IDX, FM)                                                                                       \
   do {                                                                                                                 \
-    ACFM_CUDA_OK(cudaFuncSetAttribute(raster_soft_bwd_kernel<IDX, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total)); \
+    static std::atomic<int> smem_set[kAcfmMaxDevices];                                                                 \
+    ACFM_CUDA_OK(acfm_ensure_smem(raster_soft_bwd_kernel<IDX, FM>, L.total, smem_set));                                \
     raster_soft_bwd_kernel<IDX, FM><<<(int)ctas, 128, L.total, st>>>(p);                                               \
   } while (0)
   if (faces_i64) { if (from_mask) ACFM_LAUNCH_BWD(long long, true); else ACFM_LAUNCH_BWD(long long, false); }

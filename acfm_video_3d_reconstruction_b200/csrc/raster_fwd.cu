@@ -690,7 +690,8 @@ int fwd_pick_config(int V, int F, int K, int* smem_bytes, int* cap_out) {
 template <int NWARPS, typename IdxT>
 int launch_fwd(const RasterParams& p, int smem, int ctas, cudaStream_t st) {
   auto kern = raster_fwd_kernel<NWARPS, IdxT>;
-  ACFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static std::atomic<int> smem_set[kAcfmMaxDevices];
+  ACFM_CUDA_OK(acfm_ensure_smem(kern, smem, smem_set));
   kern<<<ctas, NWARPS * 32, smem, st>>>(p);
   ACFM_LAUNCH_OK("raster_fwd_kernel");
   return ACFM_OK;

@@ -323,7 +323,8 @@ extern "C" int acfm_bds_loss_fwd(const float* verts, int vert_stride, const floa
   ACFM_REQUIRE(verts && vis && bds, ACFM_ERR_BAD_ARG, "acfm_bds_loss_fwd: null input");
   const int smem = V * 12;
   ACFM_REQUIRE(smem <= 200 * 1024, ACFM_ERR_UNSUPPORTED, "acfm_bds_loss_fwd: V=%d too large", V);
-  if (smem > 48 * 1024) ACFM_CUDA_OK(cudaFuncSetAttribute(bds_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static std::atomic<int> smem_set[kAcfmMaxDevices];
+  if (smem > 48 * 1024) ACFM_CUDA_OK(acfm_ensure_smem(bds_fwd_kernel, smem, smem_set));
   bds_fwd_kernel<<<dim3((S + kThreads - 1) / kThreads, N), kThreads, smem, st>>>(verts, vert_stride, vis, bds, (const long long*)sel, NB, V, P, S, loss, argmin);
   ACFM_LAUNCH_OK("bds_fwd_kernel");
   return ACFM_OK;

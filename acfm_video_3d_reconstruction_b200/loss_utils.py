@@ -173,16 +173,18 @@ class _BdsLoss(torch.autograd.Function):
         return gv, None, None, None
 
 
-def bds_loss(verts, bds, faces, pix_to_face, reduce=True, n_samples=1000, k=1):
+def bds_loss(verts, bds, faces, pix_to_face, reduce=True, n_samples=1000, k=1, indices=None):
     """loss_utils.py:204-237.  verts (N,V,2|3) projected vertices, bds (NB|N,P,3) boundary points [x,y,mask],
     faces (N,F,3), pix_to_face (N,H,W,K).  Like the reference, up to n_samples boundary points are drawn with
-    torch.randperm from the default (CPU) generator on every call."""
+    torch.randperm from the default (CPU) generator on every call — unless `indices` (int64, on the device) is given,
+    which keeps the call free of host work (CUDA-graph capture, predictor.PostOptimizer)."""
     if k != 1:
         raise ValueError("bds_loss: only k=1 (the reference's only call) is implemented")
     _lib.require_cuda(verts, bds, faces, pix_to_face)
-    indices = torch.randperm(bds.shape[1])[:n_samples]
+    if indices is None:
+        indices = torch.randperm(bds.shape[1])[:n_samples].to(verts.device)
     vis = visible_vertices(pix_to_face, faces, verts.shape[1])
-    loss = _BdsLoss.apply(verts, vis, bds, indices.to(verts.device))
+    loss = _BdsLoss.apply(verts, vis, bds, indices.contiguous())
     return loss.mean() if reduce else loss
 
 

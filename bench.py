@@ -286,6 +286,7 @@ def run_ours(args):
             pass
     if world == 1:
         out["target_maps"] = target_maps_bench(hp, cfg, peak, cpu=not args.no_cpu_baseline)
+        out["post_optimize"] = post_optimize_bench(hp, cfg, cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(cfg, hp.wl, hp.h_target, hp.h_edt, max_seconds=20.0)
     print(json.dumps(out), flush=True)
@@ -327,6 +328,42 @@ def target_maps_bench(hp, cfg, peak, cpu=True, iters=10):
         dt = time.time() - t
         out["cpu_baseline"] = {"value": len(mn) / dt, "unit": "masks/s", "cores": 1, "kind": "port",
                                "sample": f"{len(mn)} masks, scipy.ndimage EDT x3 + restated find_boundaries, serial as in set_input"}
+    return out
+
+
+def post_optimize_bench(hp, cfg, cpu=True, frames=12, iters=20):
+    """Side measurement (not part of `value`): the test-time post-optimisation loop (SURVEY.md 8f rank 2,
+    predictor.py:287-349) at the reference's eval batch of 12 frames, 20 Adam iterations, CUDA-graph replay vs eager
+    launches vs the CPU restatement (bounded to 2 iterations)."""
+    from acfm_video_3d_reconstruction_b200 import image_utils
+    from acfm_video_3d_reconstruction_b200.predictor import PostOptimizer
+    d = hp.device
+    masks = hp.h_target[:frames].to(d)
+    edts = image_utils.compute_dt_barrier(masks)
+    bds = image_utils.compute_boundaries(masks)
+    lbs = torch.softmax(hp.lbs_param.detach(), dim=0)
+    delta = hp.h_delta[:frames].to(d)
+    cams = hp.h_cams[:frames].to(d)
+    gen = torch.Generator().manual_seed(0)
+    sel = torch.stack([torch.randperm(bds.shape[1], generator=gen)[:1000] for _ in range(iters)]).to(d)
+    out = {"frames": frames, "iters": iters, "unit": "ms per iteration"}
+    for name, graph in (("eager", False), ("cuda_graph", True)):
+        po = PostOptimizer(img_size=cfg["img"], offset_z=cfg["offset_z"], num_optim_iter=iters, of_loss_wt=0.0, use_cuda_graph=graph)
+        po.renderer.faces_per_pixel = cfg["K"]
+        po.run(hp.mean_v, lbs, hp.L, delta, cams, masks, edts, bds, hp.faces, sample_indices=sel)       # warm-up
+        torch.cuda.synchronize()
+        t = time.time()
+        r = po.run(hp.mean_v, lbs, hp.L, delta, cams, masks, edts, bds, hp.faces, sample_indices=sel)
+        torch.cuda.synchronize()
+        out[name] = (time.time() - t) * 1e3 / iters
+        out["loss_first_last"] = [float(r["losses"][0]), float(r["losses"][-1])]
+    if cpu:
+        from oracle import predictor_ref
+        t = time.time()
+        predictor_ref.post_optimize(hp.mean_v.cpu(), lbs.cpu(), hp.L.cpu(), delta.cpu(), cams.cpu(), masks.cpu(), edts.cpu(), bds.cpu(),
+                                    hp.faces.cpu().expand(frames, -1, -1).contiguous(), sel[:2].cpu(), cfg["img"], offset_z=cfg["offset_z"])
+        out["cpu_baseline"] = {"value": (time.time() - t) * 1e3 / 2, "unit": "ms per iteration", "kind": "port",
+                               "sample": "2 iterations, oracle/predictor_ref.py (reference's batched solve + restated CPU rasterizer)"}
     return out
 
 
@@ -380,7 +417,7 @@ def _oracle_step(wl, cfg, frames, threads, target, edt):
     # ---- backward: blend + rasterizer (C oracle), then projection / deformation (torch autograd) ----
     g_ndc = orc.neural_renderer_mask_backward(fr, faces, mask.grad.numpy())
     ndc_t.backward(torch.from_numpy(g_ndc))
-    return float(total), delta.grad, cams.grad, lbs_param.grad
+    return float(total.detach()), delta.grad, cams.grad, lbs_param.grad
 
 
 def cpu_baseline(cfg, wl, target, edt, max_seconds=20.0):
