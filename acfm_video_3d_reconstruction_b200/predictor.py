@@ -25,6 +25,7 @@ class PostOptimizer:
         self.num_optim_iter, self.optimize_camera, self.lr = num_optim_iter, optimize_camera, lr
         self.w = dict(mask=mask_loss_wt, bds_reg=boundaries_reg_wt, edt=edt_reg_wt, bdt=bdt_reg_wt, of=of_loss_wt)
         self.n_samples, self.use_cuda_graph = n_samples, use_cuda_graph
+        self._cache = {}
 
     # one evaluation of the objective (predictor.py:301-343)
     def _objective(self, st, sel):
@@ -55,7 +56,10 @@ class PostOptimizer:
         cam_pred (NB,7) [s,tx,ty,q]; masks (NB,H,W); edts_barrier (NB,1,H,W)|(NB,H,W); boundaries (NB,P,3);
         faces (NB|1,F,3); optical_flows (NB/T,T,H,W,2) already flipped and masked as predictor.py:334, or None.
         sample_indices (num_optim_iter, S) int64 boundary-point draws (default: torch.randperm per iteration, as the
-        reference).  Returns dict(pred_v, cam_pred, delta_v_res, losses (num_optim_iter,), mask_pred)."""
+        reference).  Returns dict(pred_v, cam_pred, delta_v_res, losses (num_optim_iter,), mask_pred).
+
+        With use_cuda_graph the captured iteration is cached per input shape: later calls copy their inputs into the
+        graph's static buffers, reset the Adam state and replay (capture + instantiation cost ~1 s, once)."""
         dev = mean_v.device
         NB = delta_v_res.shape[0]
         P = boundaries.shape[1]
@@ -65,48 +69,91 @@ class PostOptimizer:
         sample_indices = sample_indices.to(dev)
         with torch.no_grad():
             W = deform.skinning_matrix(lbs.detach(), L.detach())
-        st = dict(mean_v=mean_v.detach(), W=W, faces=faces if faces.shape[0] == NB else faces[:1].expand(NB, -1, -1),
-                  masks=masks, edts=edts_barrier.reshape(NB, -1), boundaries=boundaries, flows=optical_flows,
-                  num_frames=num_frames, cam=cam_pred.detach())
-        st["delta"] = delta_v_res.detach().clone().requires_grad_(True)
+        faces_nb = faces if faces.shape[0] == NB else faces[:1].expand(NB, -1, -1)
+        graph = self.use_cuda_graph and iters > 3
+        # boundary lists have a data-dependent length: pad to a multiple of 256 (mask 0 entries contribute nothing) so
+        # that the cached graph is reused across batches
+        Pcap = -(-P // 256) * 256 if graph else P
+        if Pcap != P:
+            pad = torch.zeros((boundaries.shape[0], Pcap - P, 3), dtype=boundaries.dtype, device=dev)
+            boundaries = torch.cat([boundaries, pad], 1)
+        inputs = dict(mean_v=mean_v.detach(), W=W, faces=faces_nb.contiguous(), masks=masks, edts=edts_barrier.reshape(NB, -1),
+                      boundaries=boundaries, cam=cam_pred.detach(), delta0=delta_v_res.detach(), sel=sample_indices)
+        if optical_flows is not None:
+            inputs["flows"] = optical_flows
+        key = (str(dev), num_frames, self.optimize_camera, tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(inputs.items())))
+        ctx = self._cache.get(key) if graph else None
+        if ctx is None:
+            ctx = self._build(inputs, num_frames, graph, dev)
+            if graph:
+                self._cache[key] = ctx
+        return self._execute(ctx, inputs, iters)
+
+    def _build(self, inputs, num_frames, graph, dev):
+        st = {k: v.clone() for k, v in inputs.items() if k not in ("delta0", "sel")}     # static buffers
+        st.setdefault("flows", None)
+        st["num_frames"] = num_frames
+        st["delta"] = inputs["delta0"].clone().requires_grad_(True)
         params = [st["delta"]]
         if self.optimize_camera:
-            st["scale"] = cam_pred[:, :1].detach().clone().requires_grad_(True)
-            st["trans"] = cam_pred[:, 1:3].detach().clone().requires_grad_(True)
-            st["quat"] = cam_pred[:, 3:].detach().clone().requires_grad_(True)
+            st["scale"] = inputs["cam"][:, :1].clone().requires_grad_(True)
+            st["trans"] = inputs["cam"][:, 1:3].clone().requires_grad_(True)
+            st["quat"] = inputs["cam"][:, 3:].clone().requires_grad_(True)
             params += [st["scale"], st["trans"], st["quat"]]
-        graph = self.use_cuda_graph and iters > 3
-        opt = torch.optim.Adam(params, lr=self.lr, capturable=graph)
-        losses = torch.zeros(iters, device=dev)
-        step_idx = torch.zeros(1, dtype=torch.long, device=dev)
-        sel_buf = torch.empty_like(sample_indices[0])
+        ctx = dict(st=st, params=params, graph=None, sel_all=inputs["sel"].clone(),
+                   opt=torch.optim.Adam(params, lr=self.lr, capturable=graph),
+                   losses=torch.zeros(inputs["sel"].shape[0], device=dev), step_idx=torch.zeros(1, dtype=torch.long, device=dev),
+                   sel_buf=torch.empty_like(inputs["sel"][0]), dev=dev, want_graph=graph)
+        return ctx
 
-        def iteration():
-            sel_buf.copy_(sample_indices.index_select(0, step_idx)[0])
-            total, _, _, _ = self._objective(st, sel_buf)
-            opt.zero_grad(set_to_none=True)
-            total.backward()
-            opt.step()
-            losses.index_copy_(0, step_idx, total.detach().reshape(1))
-            step_idx.add_(1)
+    def _iteration(self, ctx):
+        st = ctx["st"]
+        ctx["sel_buf"].copy_(ctx["sel_all"].index_select(0, ctx["step_idx"])[0])
+        total, _, _, _ = self._objective(st, ctx["sel_buf"])
+        ctx["opt"].zero_grad(set_to_none=True)
+        total.backward()
+        ctx["opt"].step()
+        ctx["losses"].index_copy_(0, ctx["step_idx"], total.detach().reshape(1))
+        ctx["step_idx"].add_(1)
 
-        if not graph:
+    def _execute(self, ctx, inputs, iters):
+        st, dev = ctx["st"], ctx["dev"]
+        with torch.no_grad():   # load this call's inputs into the static buffers, reset the optimiser
+            for k, v in inputs.items():
+                if k in ("delta0", "sel"):
+                    continue
+                st[k].copy_(v)
+            st["delta"].copy_(inputs["delta0"])
+            if self.optimize_camera:
+                st["scale"].copy_(inputs["cam"][:, :1]); st["trans"].copy_(inputs["cam"][:, 1:3]); st["quat"].copy_(inputs["cam"][:, 3:])
+            ctx["sel_all"].copy_(inputs["sel"])
+            ctx["losses"].zero_(); ctx["step_idx"].zero_()
+            for state in ctx["opt"].state.values():
+                for v in state.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        if not ctx["want_graph"]:
             for _ in range(iters):
-                iteration()
+                self._iteration(ctx)
         else:
-            # eager warm-up on a side stream (allocator + lazy CUDA initialisation), then capture one iteration and replay
-            warm = 3
-            s = torch.cuda.Stream(device=dev)
-            s.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(s):
-                for _ in range(warm):
-                    iteration()
-            torch.cuda.current_stream(dev).wait_stream(s)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                iteration()
-            for _ in range(iters - warm):   # capture records the iteration without running it
-                g.replay()
+            done = 0
+            if ctx["graph"] is None:
+                # eager warm-up on a side stream (allocator + lazy initialisation), then capture one iteration
+                warm = 3
+                s = torch.cuda.Stream(device=dev)
+                s.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(s):
+                    for _ in range(warm):
+                        self._iteration(ctx)
+                torch.cuda.current_stream(dev).wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):   # records the iteration without running it
+                    self._iteration(ctx)
+                ctx["graph"] = g
+                done = warm
+            for _ in range(iters - done):
+                ctx["graph"].replay()
         with torch.no_grad():
-            _, pred_v, cam, mask_pred = self._objective(st, sample_indices[-1].contiguous())
-        return dict(pred_v=pred_v, cam_pred=cam, delta_v_res=st["delta"].detach(), losses=losses, mask_pred=mask_pred)
+            _, pred_v, cam, mask_pred = self._objective(st, ctx["sel_all"][-1].contiguous())
+        return dict(pred_v=pred_v, cam_pred=cam, delta_v_res=st["delta"].detach().clone(), losses=ctx["losses"].clone(),
+                    mask_pred=mask_pred)
