@@ -53,6 +53,10 @@ SIGNATURES = {
     "acfm_edt_fwd": [_c_vp, _c_int, _c_int, _c_int, _c_f, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_boundaries_count": [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
     "acfm_boundaries_write": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_laplacian_smoothing_fwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
+    "acfm_laplacian_smoothing_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_edge_rigidity_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_edge_rigidity_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
     "acfm_raster_fwd_launch_info": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],
 }
 

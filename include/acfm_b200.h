@@ -239,6 +239,25 @@ int acfm_boundaries_count(const float* masks, int NB, int H, int W, int* row_off
 int acfm_boundaries_write(const float* masks, const int* row_offsets, const int* totals, int NB, int H, int W, int max_bd,
                           float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Shape priors on the deformed meshes.
+ * acfm_laplacian_smoothing_*: pytorch3d.loss.mesh_laplacian_smoothing(meshes, method="cot") (PyTorch3D 0.3.0; call site
+ * multiframe/main.py:699-704).  verts (N,V,3); faces as in acfm_raster_fwd.  loss (N): per-mesh (1/V) sum_i |l_i| — the
+ * caller returns loss.sum()/N.  unit (N,V,4) (saved for the backward) and workspace (N,V,4) are caller-owned floats.
+ * The cotangent weights are constants in the backward, as under the reference's no_grad.
+ * acfm_edge_rigidity_*: loss_utils.locally_rigid_fn (multiframe/nnutils/loss_utils.py:150-164).  tmpl (NT,V,3) read at
+ * n % NT; edges (E,2) int64|int32 unique undirected edges (Meshes.edges_packed of one mesh).  loss (N): per-mesh
+ * sum_e (|v_a-v_b| - |t_a-t_b|)^2 — the caller returns loss.sum()/N.  grad_tmpl (NT,V,3) may be NULL.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_laplacian_smoothing_fwd(const float* verts, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                                 int F, float* loss, float* unit, float* workspace, void* stream);
+int acfm_laplacian_smoothing_bwd(const float* verts, const void* faces, int faces_i64, int64_t faces_batch_stride,
+                                 const float* unit, const float* grad_loss, int N, int V, int F, float* grad_verts, void* stream);
+int acfm_edge_rigidity_fwd(const float* verts, const float* tmpl, const void* edges, int edges_i64, int N, int NT, int V, int E,
+                           float* loss, void* stream);
+int acfm_edge_rigidity_bwd(const float* verts, const float* tmpl, const void* edges, int edges_i64, const float* grad_loss, int N,
+                           int NT, int V, int E, float* grad_verts, float* grad_tmpl, void* stream);
+
 /* Query: dynamic shared memory (bytes) and CTAs the forward rasterizer launches for a shape
  * (host-only helper used by bench.py for the launch/roofline accounting). */
 int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes,

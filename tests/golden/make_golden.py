@@ -3,7 +3,7 @@
 box, so tests only ever read the .npz files written here.
 
   python tests/golden/make_golden.py            # everything
-  python tests/golden/make_golden.py reproj      # only the named sections (base | reproj | targets)
+  python tests/golden/make_golden.py reproj      # only the named sections (base | reproj | targets | priors)
 
 What is pinned to the reference's own code:
   templates.npz   verts/faces of the reference's template meshes (monocular/meshes/bird_aligned.obj,
@@ -16,6 +16,9 @@ What is pinned to the reference's own code:
   targets.npz     utils/image.py: compute_dt, compute_dt_barrier, compute_boundaries run by the reference's own code
                   (scipy present; cv2 stubbed — unused on this path; skimage absent: find_boundaries is restated from its
                   published implementation, grey_dilation != grey_erosion over the connectivity-1 footprint)
+  priors.npz      nnutils/loss_utils.py: locally_rigid_fn run by the reference's own code on a duck-typed packed Meshes;
+                  mesh_laplacian_smoothing(method="cot"): PyTorch3D 0.3.0's few lines restated around the reference's own
+                  geom_utils.laplacian_cot (values + fp64 gradients)
 What is NOT pinned upstream (PyTorch3D 0.3.0 is not installable: parity unpinned):
   raster_small.npz  fragments / masks / gradients from oracle/ itself — a regression pin of the
                     restated algorithm only.
@@ -186,8 +189,70 @@ def targets():
     np.savez_compressed(os.path.join(HERE, "targets.npz"), **out)
 
 
+class _PackedMeshes:
+    """Batch of N meshes sharing one topology, with the packed accessors locally_rigid_fn / laplacian_cot use."""
+
+    def __init__(self, verts, faces):
+        self.N, self.V = verts.shape[0], verts.shape[1]
+        self.v, self.f, self.device = verts, faces, verts.device
+        e = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], 0)
+        self.e = torch.unique(torch.sort(e, dim=1)[0], dim=0)
+
+    def __len__(self):
+        return self.N
+
+    def isempty(self):
+        return False
+
+    def verts_packed(self):
+        return self.v.reshape(-1, 3)
+
+    def faces_packed(self):
+        return (self.f[None] + torch.arange(self.N)[:, None, None] * self.V).reshape(-1, 3)
+
+    def edges_packed(self):
+        return (self.e[None] + torch.arange(self.N)[:, None, None] * self.V).reshape(-1, 2)
+
+
+def _laplacian_smoothing_cot(meshes):
+    """pytorch3d.loss.mesh_laplacian_smoothing(meshes, method="cot"), v0.3.0, around the reference's laplacian_cot."""
+    N = len(meshes)
+    verts_packed = meshes.verts_packed()
+    weights = torch.full((verts_packed.shape[0],), 1.0 / meshes.V, dtype=verts_packed.dtype)
+    with torch.no_grad():   # the reference's laplacian_cot is float32-only; the weights are constants of the loss
+        L, _ = ref_geom.laplacian_cot(_PackedMeshes(meshes.v.detach().float(), meshes.f))
+        norm_w = torch.sparse.sum(L, dim=1).to_dense().view(-1, 1)
+        idx = norm_w > 0
+        norm_w[idx] = 1.0 / norm_w[idx]
+        L, norm_w = L.to(verts_packed.dtype), norm_w.to(verts_packed.dtype)
+    loss = L.mm(verts_packed) * norm_w - verts_packed
+    return (loss.norm(dim=1) * weights).sum() / N
+
+
+def priors():
+    t = np.load(os.path.join(HERE, "templates.npz"))
+    gen = torch.Generator().manual_seed(21)
+    hv, hf = torch.from_numpy(t["horse_v"]), torch.from_numpy(t["horse_f"])
+    N = 3
+    X = hv[None].repeat(N, 1, 1) + 0.03 * torch.randn(N, hv.shape[0], 3, generator=gen)
+    out = {"X": X.numpy()}
+    rigid = ref_loss.locally_rigid_fn(_PackedMeshes(X, hf), _PackedMeshes(hv[None].repeat(N, 1, 1), hf))
+    out["rigid"] = rigid.numpy()
+    Xd, td = X.double().requires_grad_(True), hv.double().requires_grad_(True)
+    ref_loss.locally_rigid_fn(_PackedMeshes(Xd, hf), _PackedMeshes(td[None].repeat(N, 1, 1), hf)).backward()
+    out.update(rigid_grad_X=Xd.grad.numpy(), rigid_grad_t=td.grad.numpy())
+    out["smooth"] = _laplacian_smoothing_cot(_PackedMeshes(X, hf)).numpy()
+    Xd = X.double().requires_grad_(True)
+    sm = _laplacian_smoothing_cot(_PackedMeshes(Xd, hf))
+    sm.backward()
+    out.update(smooth64=sm.detach().numpy(), smooth_grad_X=Xd.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, "priors.npz"), **out)
+
+
 def main():
-    sections = set(sys.argv[1:]) or {"base", "reproj", "targets"}
+    sections = set(sys.argv[1:]) or {"base", "reproj", "targets", "priors"}
+    if "priors" in sections:
+        priors()
     if "targets" in sections:
         targets()
     if "reproj" in sections:

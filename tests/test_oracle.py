@@ -219,3 +219,18 @@ def test_target_maps_restatement_vs_reference_golden():
     assert np.array_equal(tr.edt_bruteforce(m == 1), np.rint(g["dt_raw"][0] ** 2).astype(np.int64))
     n = np.arange(0, 2 * 1024 * 1024 + 1, dtype=np.float64)
     assert np.array_equal(np.sqrt(n).astype(np.float32), np.sqrt(n.astype(np.float32)))
+
+
+def test_prior_losses_restatement_vs_reference_golden():
+    g = util.golden("priors.npz")
+    hv, hf = util.template("horse")
+    hv, hf = torch.from_numpy(hv), torch.from_numpy(hf)
+    X = torch.from_numpy(g["X"])
+    assert np.allclose(torch_ref.locally_rigid(X, hv, hf).numpy(), g["rigid"], rtol=1e-5)
+    assert np.allclose(torch_ref.laplacian_smoothing_cot(X, hf).numpy(), g["smooth"], rtol=1e-5)
+    Xd, td = X.double().requires_grad_(True), hv.double().requires_grad_(True)
+    torch_ref.locally_rigid(Xd, td, hf).backward()
+    assert util.rel_err(Xd.grad.numpy(), g["rigid_grad_X"]) < 1e-9 and util.rel_err(td.grad.numpy(), g["rigid_grad_t"]) < 1e-9
+    Xd = X.double().requires_grad_(True)
+    torch_ref.laplacian_smoothing_cot(Xd, hf).backward()
+    assert util.rel_err(Xd.grad.numpy(), g["smooth_grad_X"]) < 1e-4   # the constant weights are fp32 on both sides (summation order differs)
