@@ -66,11 +66,12 @@ struct RasterParams {
 
 // shared-memory carve-up, identical on host and device
 struct FwdSmem {
-  int off_red, off_hist, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
+  int off_ndc, off_red, off_hist, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
   int w_k, w_d, w_q, w_cnt;  // offsets inside one warp's slab
   int KS;                         // per-lane list stride (odd)
   __host__ __device__ FwdSmem(int V, int F, int K, int nwarps, int cap) {
     int o = 32;  // mbarrier + counters
+    off_ndc = o; o += 2 * kRegion * 4;  // pixel-centre NDC coordinates of the region's columns and rows
     off_red = o; o += nwarps * 32;
     off_hist = o; o += kZBuckets * 4;
     off_rlist = o; o += ((F * 2 + 15) / 16) * 16;  // ushort per region face
@@ -302,6 +303,8 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   int* rcount = reinterpret_cast<int*>(smem + 8);
   int* next_tile = reinterpret_cast<int*>(smem + 12);
+  float* ndc_x = reinterpret_cast<float*>(smem + L.off_ndc);  // [kRegion] columns, then [kRegion] rows
+  float* ndc_y = ndc_x + kRegion;
   float* red = reinterpret_cast<float*>(smem + L.off_red);
   int* hist = reinterpret_cast<int*>(smem + L.off_hist);
   unsigned short* rlist = reinterpret_cast<unsigned short*>(smem + L.off_rlist);
@@ -424,7 +427,12 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
   }
   __syncthreads();
 
-  // ---- 3. per-region face records ------------------------------------------------------------------------
+  // ---- 3. per-region face records; exact pixel-centre coordinates of the region (one division each, here only) ----
+  if (tid < 2 * kRegion) {
+    const int i = tid & (kRegion - 1);
+    if (tid < kRegion) ndc_x[i] = pix_to_ndc(p.W - 1 - min(px0 + i, p.W - 1), p.W);
+    else ndc_y[i] = pix_to_ndc(p.H - 1 - min(py0 + i, p.H - 1), p.H);
+  }
   const int nrec = min(nlist, cap);
   for (int j = tid; j < nrec; j += NT) {
     const int f = rlist[j];
@@ -465,15 +473,57 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
     const int tx0 = px0 + (t % tiles_x) * kTileW, ty0 = py0 + (t / tiles_x) * kTileH;
     const int xi = tx0 + (lane & 7), yi = ty0 + (lane >> 3);
     const bool valid = xi < p.W && yi < p.H;
-    const float xf = pix_to_ndc(p.W - 1 - xi, p.W), yf = pix_to_ndc(p.H - 1 - yi, p.H);
-    const float t_xhi = pix_to_ndc(p.W - 1 - tx0, p.W), t_xlo = pix_to_ndc(p.W - 1 - min(tx0 + kTileW - 1, p.W - 1), p.W);
-    const float t_yhi = pix_to_ndc(p.H - 1 - ty0, p.H), t_ylo = pix_to_ndc(p.H - 1 - min(ty0 + kTileH - 1, p.H - 1), p.H);
+    const int lx0 = tx0 - px0, ly0 = ty0 - py0;  // tile origin inside the region
+    const float xf = ndc_x[lx0 + (lane & 7)], yf = ndc_y[ly0 + (lane >> 3)];
+    const float t_xhi = ndc_x[lx0], t_xlo = ndc_x[lx0 + kTileW - 1];  // table entries past the image edge repeat the last pixel
+    const float t_yhi = ndc_y[ly0], t_ylo = ndc_y[ly0 + kTileH - 1];
 
     int cnt = 0, qn = 0;
     unsigned long long last = 0ull;
 
-    // (c) evaluate: each lane pops its own queue
-    auto drain = [&]() {
+    // (a)-(c): fill the per-lane queues face by face; drain them when one is full or the faces run out (one drain site)
+    int c0 = 0, cbase = 0;
+    unsigned m = 0u;
+    bool more = true;
+    do {
+      bool full = false;
+      while (!full) {
+        if (m == 0u) {
+          if (c0 >= nrec) { more = false; break; }
+          // (a) scan: lane = face; tile-level bbox + edge-equation culling
+          const int j = c0 + lane;
+          bool hit = false;
+          if (j < nrec) {
+            const float4 bb = recA[j];
+            hit = !(t_xlo > bb.y) && !(t_xhi < bb.x) && !(t_ylo > bb.w) && !(t_yhi < bb.z);
+            if (hit) {
+              const float4 ga = recA[cap + j], gb = recA[2 * cap + j];
+              const float gc = recA[3 * cap + j].x;
+              const float m0 = fmaf(ga.x, ga.x > 0.f ? t_xhi : t_xlo, fmaf(ga.y, ga.y > 0.f ? t_yhi : t_ylo, ga.z));
+              const float m1 = fmaf(ga.w, ga.w > 0.f ? t_xhi : t_xlo, fmaf(gb.x, gb.x > 0.f ? t_yhi : t_ylo, gb.y));
+              const float m2 = fmaf(gb.z, gb.z > 0.f ? t_xhi : t_xlo, fmaf(gb.w, gb.w > 0.f ? t_yhi : t_ylo, gc));
+              hit = !(m0 < -1.0f) && !(m1 < -1.0f) && !(m2 < -1.0f);
+            }
+          }
+          m = __ballot_sync(0xffffffffu, hit);
+          cbase = c0;
+          c0 += 32;
+          continue;
+        }
+        // (b) filter: lane = pixel, face uniform; survivors are queued per lane
+        const int jj = cbase + __ffs(m) - 1;
+        m &= m - 1;
+        const float4 bb = recA[jj], ga = recA[cap + jj], gb = recA[2 * cap + jj];
+        const float gc = recA[3 * cap + jj].x;
+        bool cand = valid && !(xf > bb.y) && !(xf < bb.x) && !(yf > bb.w) && !(yf < bb.z);
+        const float g0 = fmaf(ga.x, xf, fmaf(ga.y, yf, ga.z));
+        const float g1 = fmaf(ga.w, xf, fmaf(gb.x, yf, gb.y));
+        const float g2 = fmaf(gb.z, xf, fmaf(gb.w, yf, gc));
+        cand = cand && !(g0 < -1.0f) && !(g1 < -1.0f) && !(g2 < -1.0f);
+        if (cand) queue[(qn++) * 32 + lane] = (unsigned char)jj;
+        full = __any_sync(0xffffffffu, qn == kQueue);
+      }
+      // (c) evaluate: each lane pops its own queue
       const int qmax = __reduce_max_sync(0xffffffffu, qn);
       for (int i = 0; i < qmax; ++i) {
         if (i < qn) {
@@ -490,42 +540,7 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
         }
       }
       qn = 0;
-    };
-
-    for (int c0 = 0; c0 < nrec; c0 += 32) {
-      // (a) scan: lane = face; tile-level bbox + edge-equation culling
-      const int j = c0 + lane;
-      bool hit = false;
-      if (j < nrec) {
-        const float4 bb = recA[j];
-        hit = !(t_xlo > bb.y) && !(t_xhi < bb.x) && !(t_ylo > bb.w) && !(t_yhi < bb.z);
-        if (hit) {
-          const float4 ga = recA[cap + j], gb = recA[2 * cap + j];
-          const float gc = recA[3 * cap + j].x;
-          const float m0 = fmaf(ga.x, ga.x > 0.f ? t_xhi : t_xlo, fmaf(ga.y, ga.y > 0.f ? t_yhi : t_ylo, ga.z));
-          const float m1 = fmaf(ga.w, ga.w > 0.f ? t_xhi : t_xlo, fmaf(gb.x, gb.x > 0.f ? t_yhi : t_ylo, gb.y));
-          const float m2 = fmaf(gb.z, gb.z > 0.f ? t_xhi : t_xlo, fmaf(gb.w, gb.w > 0.f ? t_yhi : t_ylo, gc));
-          hit = !(m0 < -1.0f) && !(m1 < -1.0f) && !(m2 < -1.0f);
-        }
-      }
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      // (b) filter: lane = pixel, face uniform; survivors are queued per lane
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const int jj = c0 + src;
-        const float4 bb = recA[jj], ga = recA[cap + jj], gb = recA[2 * cap + jj];
-        const float gc = recA[3 * cap + jj].x;
-        bool cand = valid && !(xf > bb.y) && !(xf < bb.x) && !(yf > bb.w) && !(yf < bb.z);
-        const float g0 = fmaf(ga.x, xf, fmaf(ga.y, yf, ga.z));
-        const float g1 = fmaf(ga.w, xf, fmaf(gb.x, yf, gb.y));
-        const float g2 = fmaf(gb.z, xf, fmaf(gb.w, yf, gc));
-        cand = cand && !(g0 < -1.0f) && !(g1 < -1.0f) && !(g2 < -1.0f);
-        if (cand) queue[(qn++) * 32 + lane] = (unsigned char)jj;
-        if (__any_sync(0xffffffffu, qn == kQueue)) drain();
-      }
-    }
-    drain();
+    } while (more);
 
     // overflow: region faces without a record (face-uniform evaluation, set-up broadcast by shuffles)
     for (int c0 = nrec; c0 < nlist; c0 += 32) {
@@ -645,7 +660,7 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
           const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
           const float x0 = gverts[i0 * 3], y0 = gverts[i0 * 3 + 1], x1 = gverts[i1 * 3], y1 = gverts[i1 * 3 + 1];
           const float x2 = gverts[i2 * 3], y2 = gverts[i2 * 3 + 1];
-          const float pxf = pix_to_ndc(p.W - 1 - (tx0 + col), p.W), pyf = pix_to_ndc(p.H - 1 - (ty0 + row), p.H);
+          const float pxf = ndc_x[lx0 + col], pyf = ndc_y[ly0 + row];
           const float den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), ACFM_K_EPS);
           b0 = fdiv(edge_fn(pxf, pyf, x1, y1, x2, y2), den);
           b1 = fdiv(edge_fn(pxf, pyf, x2, y2, x0, y0), den);
