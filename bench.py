@@ -6,7 +6,7 @@
          bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over one batch of synthetic input on every rank:
-  skinning matrix (one V x V solve) -> fused handle deformation + G-hypothesis projection -> tile-binned soft
+  skinning matrix (Woodbury update of a once-inverted Laplacian term, fp64) -> fused handle deformation + G-hypothesis projection -> tile-binned soft
   rasterizer (fragments pix_to_face/zbuf/dists materialised, fused silhouette blend) -> fused mask losses
   (l1 + edt) -> hypothesis softmax weighting -> backward to handle offsets, cameras and handle weights ->
   (N > 1) NCCL all-reduce of the shared-parameter gradients.
@@ -117,7 +117,8 @@ class HotPath:
         self.mean_v = wl.mean_v.to(device)
         self.lbs_param = wl.lbs_param.to(device).requires_grad_(True)
         self.L = wl.L.to(device)
-        self.LtL = self.L.t().matmul(self.L)                       # the Laplacian is fixed at init (monocular/main.py:124)
+        from acfm_video_3d_reconstruction_b200 import deform
+        self.solver = deform.HandleSolver(self.L)                  # the Laplacian is fixed at init (monocular/main.py:124)
         self.faces = wl.faces.to(device)[None]                     # shared topology, (1,F,3) int64
         # host-side (pinned) per-step inputs
         self.h_delta = wl.delta.pin_memory()
@@ -161,7 +162,7 @@ class HotPath:
         cams = cams.detach().requires_grad_(True)
         self.lbs_param.grad = None
         lbs = torch.softmax(self.lbs_param, dim=0)                 # MeshNet.get_lbs: softmax over vertices
-        W = deform.skinning_matrix(lbs, self.L, self.LtL)
+        W = deform.skinning_matrix(lbs, self.L, solver=self.solver)
         _, ndc = deform.deform_and_project(self.mean_v, W, delta, cams, offset_z=cfg["offset_z"])
         mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
         ls = loss_utils.mask_losses(mask, target, edt)
