@@ -110,6 +110,52 @@ __global__ void __launch_bounds__(256) skin_bwd_w_kernel(const float* __restrict
   if (grad_mean && k == 0) { grad_mean[v * 3] = m0; grad_mean[v * 3 + 1] = m1; grad_mean[v * 3 + 2] = m2; }
 }
 
+// ---- handle weights: softmax over VERTICES per handle (MeshNet.get_lbs, mesh_net.py:597-599) -----------------
+// x, y (V,K) row-major; one CTA per handle column.  torch's softmax over a strided dim 0 costs ~50 us at (642,32).
+__global__ void __launch_bounds__(256) softmax_cols_fwd_kernel(const float* __restrict__ x, int V, int K, float* __restrict__ y) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  float m = -INFINITY;
+  for (int v = tid; v < V; v += 256) m = fmaxf(m, x[(size_t)v * K + k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) { float a = red[0]; for (int w = 1; w < 8; ++w) a = fmaxf(a, red[w]); bc = a; }
+  __syncthreads();
+  m = bc;
+  float s = 0.0f;
+  for (int v = tid; v < V; v += 256) s += expf(x[(size_t)v * K + k] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) { float a = 0.f; for (int w = 0; w < 8; ++w) a += red[w]; bc = a; }
+  __syncthreads();
+  const float inv = 1.0f / bc;
+  for (int v = tid; v < V; v += 256) y[(size_t)v * K + k] = expf(x[(size_t)v * K + k] - m) * inv;
+}
+
+// gx = y * (gy - sum_v gy*y)
+__global__ void __launch_bounds__(256) softmax_cols_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gy, int V, int K,
+                                                               float* __restrict__ gx) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  float s = 0.0f;
+  for (int v = tid; v < V; v += 256) s += gy[(size_t)v * K + k] * y[(size_t)v * K + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) { float a = 0.f; for (int w = 0; w < 8; ++w) a += red[w]; bc = a; }
+  __syncthreads();
+  const float d = bc;
+  for (int v = tid; v < V; v += 256) gx[(size_t)v * K + k] = y[(size_t)v * K + k] * (gy[(size_t)v * K + k] - d);
+}
+
 }  // namespace
 
 extern "C" int acfm_skin_project_fwd(const float* mean_v, const float* W, const float* delta, const float* cams, int NB,
@@ -148,5 +194,23 @@ extern "C" int acfm_skin_bwd(const float* W, const float* delta, const float* gr
     skin_bwd_w_kernel<<<(V * Kk + 255) / 256, 256, 0, st>>>(grad_pred_v, delta, NB, V, Kh, grad_W, grad_mean_v);
     ACFM_LAUNCH_OK("skin_bwd_w_kernel");
   }
+  return ACFM_OK;
+}
+
+extern "C" int acfm_softmax_cols_fwd(const float* x, int V, int K, float* y, void* stream) {
+  ACFM_REQUIRE(V >= 0 && K >= 0, ACFM_ERR_BAD_ARG, "acfm_softmax_cols_fwd: bad sizes");
+  if (V == 0 || K == 0) return ACFM_OK;
+  ACFM_REQUIRE(x && y, ACFM_ERR_BAD_ARG, "acfm_softmax_cols_fwd: null pointer");
+  softmax_cols_fwd_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(x, V, K, y);
+  ACFM_LAUNCH_OK("softmax_cols_fwd_kernel");
+  return ACFM_OK;
+}
+
+extern "C" int acfm_softmax_cols_bwd(const float* y, const float* grad_y, int V, int K, float* grad_x, void* stream) {
+  ACFM_REQUIRE(V >= 0 && K >= 0, ACFM_ERR_BAD_ARG, "acfm_softmax_cols_bwd: bad sizes");
+  if (V == 0 || K == 0) return ACFM_OK;
+  ACFM_REQUIRE(y && grad_y && grad_x, ACFM_ERR_BAD_ARG, "acfm_softmax_cols_bwd: null pointer");
+  softmax_cols_bwd_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(y, grad_y, V, K, grad_x);
+  ACFM_LAUNCH_OK("softmax_cols_bwd_kernel");
   return ACFM_OK;
 }

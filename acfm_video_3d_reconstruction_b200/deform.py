@@ -35,6 +35,37 @@ class _SkinningMatrix(torch.autograd.Function):
         return g, None
 
 
+class _GetLbs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lbs_param):
+        _lib.require_cuda(lbs_param)
+        x = F_._f32c(lbs_param)
+        V, K = x.shape
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            st = _lib.lib().acfm_softmax_cols_fwd(_lib.ptr(x), V, K, _lib.ptr(y), _lib.stream_of(x))
+        _lib.check(st, "acfm_softmax_cols_fwd")
+        _lib.count()
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, = ctx.saved_tensors
+        V, K = y.shape
+        gx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            st = _lib.lib().acfm_softmax_cols_bwd(_lib.ptr(y), _lib.ptr(F_._f32c(g)), V, K, _lib.ptr(gx), _lib.stream_of(y))
+        _lib.check(st, "acfm_softmax_cols_bwd")
+        _lib.count()
+        return gx
+
+
+def get_lbs(lbs_param):
+    """MeshNet.get_lbs (mesh_net.py:597-599): softmax of the (V,Kh) handle-weight parameter over the VERTICES (dim 0)."""
+    return _GetLbs.apply(lbs_param)
+
+
 class HandleSolver:
     """Per-step solve for the skinning matrix W = (L^T L + lbs lbs^T)^-1 lbs when the Laplacian L is constant across steps
     (monocular: built once at init, monocular/main.py:124; multiframe: rebuilt every forward from a template that does not

@@ -161,7 +161,7 @@ class HotPath:
         delta = delta.detach().requires_grad_(True)
         cams = cams.detach().requires_grad_(True)
         self.lbs_param.grad = None
-        lbs = torch.softmax(self.lbs_param, dim=0)                 # MeshNet.get_lbs: softmax over vertices
+        lbs = deform.get_lbs(self.lbs_param)                       # MeshNet.get_lbs: softmax over vertices
         W = deform.skinning_matrix(lbs, self.L, solver=self.solver)
         _, ndc = deform.deform_and_project(self.mean_v, W, delta, cams, offset_z=cfg["offset_z"])
         mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)

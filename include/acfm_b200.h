@@ -69,6 +69,11 @@ int acfm_skin_project_fwd(const float* mean_v, const float* W, const float* delt
 int acfm_skin_bwd(const float* W, const float* delta, const float* grad_pred_v, int NB, int V, int Kh,
                   float* grad_delta, float* grad_W, float* grad_mean_v, void* stream);
 
+/* Handle weights: softmax over VERTICES (dim 0) of the (V,Kh) parameter — MeshNet.get_lbs
+ * (multiframe/nnutils/mesh_net.py:597-599, monocular/nnutils/mesh_net.py:468-470).  x, y, grads (V,K) row-major. */
+int acfm_softmax_cols_fwd(const float* x, int V, int K, float* y, void* stream);
+int acfm_softmax_cols_bwd(const float* y, const float* grad_y, int V, int K, float* grad_x, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Rasterization.  Replaces pytorch3d.renderer.mesh.rasterize_meshes (PyTorch3D 0.3.0, the
  * reference's third-party dependency) as reached through MeshRasterizer from

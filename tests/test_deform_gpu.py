@@ -89,3 +89,18 @@ def test_handle_solver_matches_direct_solve():
     assert not bad.ok
     assert torch.allclose(deform.skinning_matrix(lbs.cuda(), torch.eye(L.shape[0], device="cuda"), solver=bad),
                           deform.skinning_matrix(lbs.cuda(), torch.eye(L.shape[0], device="cuda")))
+
+
+def test_get_lbs_softmax_over_vertices():
+    from acfm_video_3d_reconstruction_b200 import deform
+    gen = torch.Generator().manual_seed(2)
+    for V, K in ((642, 32), (2562, 16), (7, 1)):
+        x = (3 * torch.randn(V, K, generator=gen)).requires_grad_(True)
+        w = torch.randn(V, K, generator=gen)
+        (torch.softmax(x.double(), dim=0) * w.double()).sum().backward()
+        xc = x.detach().cuda().requires_grad_(True)
+        y = deform.get_lbs(xc)
+        (y * w.cuda()).sum().backward()
+        assert util.rel_err(y.detach().cpu().numpy(), torch.softmax(x.detach().double(), 0).numpy()) < 1e-6
+        assert util.rel_err(xc.grad.cpu().numpy(), x.grad.numpy()) < 1e-5
+        assert torch.allclose(y.sum(0), torch.ones(K, device="cuda"), atol=1e-5)
