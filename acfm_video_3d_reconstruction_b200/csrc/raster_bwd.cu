@@ -44,14 +44,32 @@ struct BwdSmem {
   }
 };
 
-// d(dist)/d(a), d(dist)/d(b) for the segment ab closest to p (PointLineDistanceBackward, §9.6)
-__device__ __forceinline__ void seg_grad(float px, float py, float ax, float ay, float bx, float by, float g, int ia,
-                                         int ib, float* acc) {
+// Squared distance from p to segment ab with the clamped parameter t and the foot point q (fast arithmetic: the backward
+// is held to 1e-3 relative, not to bit parity; only the CHOICE of the closest edge has to agree with the forward, and near a
+// tie either choice has the same gradient to that tolerance).
+__device__ __forceinline__ float seg_foot(float px, float py, float ax, float ay, float bx, float by, float& t, float& qx, float& qy) {
   const float bax = bx - ax, bay = by - ay;
   const float l2 = bax * bax + bay * bay;
-  float t = (bax * (px - ax) + bay * (py - ay)) / l2;
+  t = l2 > 0.0f ? __fdividef(bax * (px - ax) + bay * (py - ay), l2) : 0.0f;
   t = fminf(fmaxf(t, 0.0f), 1.0f);
-  const float qx = (1.0f - t) * ax + t * bx, qy = (1.0f - t) * ay + t * by;
+  qx = fmaf(t, bax, ax); qy = fmaf(t, bay, ay);
+  const float dx = qx - px, dy = qy - py;
+  return dx * dx + dy * dy;
+}
+
+// gradient of one fragment's squared distance w.r.t. the two vertices of its closest edge (PointLineDistanceBackward,
+// SURVEY.md §9.6), accumulated into the CTA's (V,2) shared accumulator
+__device__ __forceinline__ void frag_grad(float px, float py, float x0, float y0, float x1, float y1, float x2, float y2, float g,
+                                          int i0, int i1, int i2, float* acc) {
+  float t01, t02, t12, qx01, qy01, qx02, qy02, qx12, qy12;
+  const float d01 = seg_foot(px, py, x0, y0, x1, y1, t01, qx01, qy01);
+  const float d02 = seg_foot(px, py, x0, y0, x2, y2, t02, qx02, qy02);
+  const float d12 = seg_foot(px, py, x1, y1, x2, y2, t12, qx12, qy12);
+  float t, qx, qy;
+  int ia, ib;
+  if (d01 <= d02 && d01 <= d12) { t = t01; qx = qx01; qy = qy01; ia = i0; ib = i1; }       // same order as the forward's min
+  else if (d02 <= d12) { t = t02; qx = qx02; qy = qy02; ia = i0; ib = i2; }
+  else { t = t12; qx = qx12; qy = qy12; ia = i1; ib = i2; }
   const float gx = g * 2.0f * (qx - px), gy = g * 2.0f * (qy - py);
   atomicAdd(acc + ia * 2, (1.0f - t) * gx);
   atomicAdd(acc + ia * 2 + 1, (1.0f - t) * gy);
@@ -113,7 +131,9 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
 
   // ---- 2. one active pixel per lane, 32 at a time, chunks pulled dynamically --------------------------
   const float inv_sigma = 1.0f / p.sigma;
+  const float inv_w = 1.0f / (float)p.W, inv_h = 1.0f / (float)p.H;
   const int nchunks = (na + 31) / 32;
+  const bool vec = (K & 3) == 0 && (((uintptr_t)p.p2f | (uintptr_t)p.dists | (FROM_MASK ? 0 : (uintptr_t)p.grad_dists)) & 15u) == 0;
   while (true) {
     int c = 0;
     if (lane == 0) c = atomicAdd(next_chunk, 1);
@@ -124,42 +144,61 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
     const int i = alist[a];
     const int xi = px0 + (i & (kRegion - 1)), yi = py0 + (i / kRegion);
     const long long pix = ((long long)n * p.H + yi) * p.W + xi;
-    const float xf = pix_to_ndc(p.W - 1 - xi, p.W), yf = pix_to_ndc(p.H - 1 - yi, p.H);
+    // pixel centre (PixToNdc); 2 ulp is plenty for the backward
+    const float xf = fmaf((float)(2 * (p.W - 1 - xi) + 1), inv_w, -1.0f), yf = fmaf((float)(2 * (p.H - 1 - yi) + 1), inv_h, -1.0f);
     const long long* pf = p.p2f + pix * K;
     const float* pd = p.dists + pix * K;
-    float alpha = 1.0f;
-    int cnt = 0;
-    for (; cnt < K; ++cnt) {
-      if (pf[cnt] < 0) break;  // lists are front-packed
-      if (FROM_MASK) alpha *= 1.0f - 1.0f / (1.0f + expf(pd[cnt] * inv_sigma));
-    }
+    const long long nF = (long long)n * p.F;
+    // d mask / d dist_k = -(prob_k / sigma) * prod_j (1 - prob_j)   (SURVEY.md §9.5); the product is 1 - mask, which the
+    // forward already formed (its rounding only matters where the product, hence the gradient, is < 1e-7 of the largest)
     float ga = 1.0f;
-    if (FROM_MASK) ga = -p.grad_mask[pix] * alpha * inv_sigma;
-    if (ga == 0.0f || cnt == 0) continue;
-    int k = (lane * 7) % cnt;  // decorrelate neighbouring pixels (see header comment)
-    for (int s = 0; s < cnt; ++s) {
-      const float d = pd[k];
-      const int f = (int)(pf[k] - (long long)n * p.F);
-      float gd;
-      if (FROM_MASK) {
-        // d mask / d dist_k = -(prob_k / sigma) * prod_j (1 - prob_j)   
-        gd = ga * (1.0f / (1.0f + expf(d * inv_sigma)));
-      } else {
-        gd = p.grad_dists[pix * K + k];
+    if (FROM_MASK) {
+      ga = -p.grad_mask[pix] * (1.0f - p.mask[pix]) * inv_sigma;
+      if (ga == 0.0f) continue;
+    }
+    if (vec) {
+      // fragments in groups of four (16-byte loads, all issued before use); lanes start at different groups so that
+      // neighbouring pixels, which see the same faces at the same depth rank, touch different vertices at the same time
+      const int groups = K >> 2;
+      int g = lane % groups;
+      for (int s = 0; s < groups; ++s) {
+        const longlong2 fa = *reinterpret_cast<const longlong2*>(pf + 4 * g);
+        const longlong2 fb = *reinterpret_cast<const longlong2*>(pf + 4 * g + 2);
+        const float4 dd = *reinterpret_cast<const float4*>(pd + 4 * g);
+        float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!FROM_MASK) gg = *reinterpret_cast<const float4*>(p.grad_dists + pix * K + 4 * g);
+        const long long fid[4] = {fa.x, fa.y, fb.x, fb.y};
+        const float dv[4] = {dd.x, dd.y, dd.z, dd.w};
+        const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
+        g = (g + 1 == groups) ? 0 : g + 1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (fid[e] < 0) break;  // lists are front-packed
+          const float d = dv[e];
+          float gd = FROM_MASK ? ga * __fdividef(1.0f, 1.0f + __expf(d * inv_sigma)) : gv[e];
+          if (gd == 0.0f) continue;
+          if (signbit(d)) gd = -gd;  // dist = inside ? -|d| : |d|
+          const ushort4 iv = sfaces[(int)(fid[e] - nF)];
+          frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd,
+                    iv.x, iv.y, iv.z, acc);
+        }
       }
-      k = (k + 1 == cnt) ? 0 : k + 1;
-      if (gd == 0.0f) continue;
-      if (signbit(d)) gd = -gd;  // dist = inside ? -|d| : |d|
-      const ushort4 iv = sfaces[f];
-      const int i0 = iv.x, i1 = iv.y, i2 = iv.z;
-      const float x0 = sv[i0 * 3], y0 = sv[i0 * 3 + 1], x1 = sv[i1 * 3], y1 = sv[i1 * 3 + 1];
-      const float x2 = sv[i2 * 3], y2 = sv[i2 * 3 + 1];
-      const float d01 = point_line_dist(xf, yf, x0, y0, x1, y1);
-      const float d02 = point_line_dist(xf, yf, x0, y0, x2, y2);
-      const float d12 = point_line_dist(xf, yf, x1, y1, x2, y2);
-      if (d01 <= d02 && d01 <= d12) seg_grad(xf, yf, x0, y0, x1, y1, gd, i0, i1, acc);
-      else if (d02 <= d01 && d02 <= d12) seg_grad(xf, yf, x0, y0, x2, y2, gd, i0, i2, acc);
-      else if (d12 <= d01 && d12 <= d02) seg_grad(xf, yf, x1, y1, x2, y2, gd, i1, i2, acc);
+    } else {
+      int cnt = 0;
+      while (cnt < K && pf[cnt] >= 0) ++cnt;  // lists are front-packed
+      if (cnt == 0) continue;
+      int k = (lane * 7) % cnt;
+      for (int s = 0; s < cnt; ++s) {
+        const float d = pd[k];
+        const int f = (int)(pf[k] - nF);
+        float gd = FROM_MASK ? ga * __fdividef(1.0f, 1.0f + __expf(d * inv_sigma)) : p.grad_dists[pix * K + k];
+        k = (k + 1 == cnt) ? 0 : k + 1;
+        if (gd == 0.0f) continue;
+        if (signbit(d)) gd = -gd;
+        const ushort4 iv = sfaces[f];
+        frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd,
+                  iv.x, iv.y, iv.z, acc);
+      }
     }
   }
   __syncthreads();
