@@ -128,8 +128,13 @@ struct FaceB {
   int flags;  // face id | den_ok << 16 | l01_ok << 17 | l02_ok << 18 | l12_ok << 19
 };
 
-// generic version: every division individually guarded, degenerate edges handled (rare faces only)
-__device__ __noinline__ bool eval_pair_generic(const FaceB& r, float xf, float yf, int clip, float blur, unsigned& zbits, float& sd) {
+// generic version: every division individually guarded, degenerate edges handled (rare faces only).  Out of line, with the
+// record passed BY VALUE and the result returned by value (depth bits, signed distance; depth bits 0xffffffff = no fragment),
+// so that the hot caller keeps its record in registers: a by-reference signature forces the caller to spill the whole record
+// to local memory on every pair, taken or not.
+constexpr unsigned kNoFragment = 0xffffffffu;
+struct FragZD { unsigned zbits; float sd; };
+__device__ __forceinline__ bool eval_pair_generic_impl(const FaceB& r, float xf, float yf, int clip, float blur, unsigned& zbits, float& sd) {
   const float dx0 = fsub(xf, r.x0), dy0 = fsub(yf, r.y0), dx1 = fsub(xf, r.x1), dy1 = fsub(yf, r.y1);
   const float dx2 = fsub(xf, r.x2), dy2 = fsub(yf, r.y2);
   const float ex01 = fsub(r.x1, r.x0), ey01 = fsub(r.y1, r.y0), ex02 = fsub(r.x2, r.x0), ey02 = fsub(r.y2, r.y0);
@@ -162,6 +167,14 @@ __device__ __noinline__ bool eval_pair_generic(const FaceB& r, float xf, float y
   return true;
 }
 
+__device__ __noinline__ FragZD eval_pair_generic(FaceB r, float xf, float yf, int clip, float blur) {
+  FragZD o;
+  o.zbits = kNoFragment; o.sd = 0.0f;
+  unsigned z; float d;
+  if (eval_pair_generic_impl(r, xf, yf, clip, blur, z, d)) { o.zbits = z; o.sd = d; }
+  return o;
+}
+
 // squared distance from p to q = a + clamp(t) * ba
 __device__ __forceinline__ float seg_dist_t(float t, float ax, float ay, float bax, float bay, float px, float py) {
   const float tt = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
@@ -178,7 +191,11 @@ __device__ __forceinline__ float seg_dist_t(float t, float ax, float ay, float b
 constexpr int kFaceFast = 0x100000;
 
 __device__ __forceinline__ bool eval_pair(const FaceB& r, float xf, float yf, int clip, float blur, unsigned& zbits, float& sd) {
-  if (!(r.flags & kFaceFast)) return eval_pair_generic(r, xf, yf, clip, blur, zbits, sd);
+  if (!(r.flags & kFaceFast)) {
+    const FragZD o = eval_pair_generic(r, xf, yf, clip, blur);
+    zbits = o.zbits; sd = o.sd;
+    return o.zbits != kNoFragment;
+  }
   const float dx0 = fsub(xf, r.x0), dy0 = fsub(yf, r.y0), dx1 = fsub(xf, r.x1), dy1 = fsub(yf, r.y1);
   const float dx2 = fsub(xf, r.x2), dy2 = fsub(yf, r.y2);
   const float ex01 = fsub(r.x1, r.x0), ey01 = fsub(r.y1, r.y0), ex02 = fsub(r.x2, r.x0), ey02 = fsub(r.y2, r.y0);
