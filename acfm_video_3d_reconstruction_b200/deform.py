@@ -97,15 +97,20 @@ class HandleSolver:
         except RuntimeError:
             self.ok = False
         self.ones = ones
+        self._sinv = {}
 
     def _pieces(self, lbs):
         U = torch.cat([lbs.detach().double(), self.ones], 1)                  # (V,Kh+1)
         PU = self.Pinv.matmul(U)
         K1 = U.shape[1]
-        s_inv = torch.ones(K1, dtype=torch.float64, device=U.device)
-        s_inv[-1] = -self.V / self.c
-        C = torch.diag(s_inv) + U.t().matmul(PU)
-        return U, PU, torch.linalg.lu_factor(C)
+        Sinv = self._sinv.get(K1)
+        if Sinv is None:   # built on the host once per handle count: nothing but launches in the steady state (graph capture)
+            d = torch.ones(K1, dtype=torch.float64)
+            d[-1] = -self.V / self.c
+            Sinv = self._sinv[K1] = torch.diag(d).to(U.device)
+        C = Sinv + U.t().matmul(PU)
+        lu, piv, _ = torch.linalg.lu_factor_ex(C, check_errors=False)   # no host sync: the step stays CUDA-graph capturable
+        return U, PU, (lu, piv)
 
     def _minv(self, pieces, B):
         U, PU, (lu, piv) = pieces

@@ -87,3 +87,40 @@ def test_cached_graph_is_reused_for_new_inputs():
     assert [v["graph"] for v in pg._cache.values()] == graphs and len(graphs) == 1
     assert np.allclose(a["losses"].cpu().numpy(), b["losses"].cpu().numpy(), rtol=1e-4)
     assert (a["losses"] != 0).all()
+
+
+def test_captured_training_step_equals_eager():
+    """graphs.CapturedStep around a full hot-path step (handle solver, deformation + multiplex projection, soft raster,
+    fused losses, hypothesis weighting, backward): replay with new inputs reproduces the eager results."""
+    from acfm_video_3d_reconstruction_b200 import deform, graphs, loss_utils, synthetic
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    wl = synthetic.Workload("bird", frames=4, G=3, handles=8, img_size=64, seed=2, offset_z=5.0)
+    dev = torch.device("cuda")
+    mean_v, L, faces = wl.mean_v.to(dev), wl.L.to(dev), wl.faces.to(dev)[None]
+    lbs_param = wl.lbs_param.to(dev).requires_grad_(True)
+    solver = deform.HandleSolver(L)
+    target = (torch.rand(4, 64, 64, device=dev) > 0.7).float()
+
+    def step(delta, cams):
+        delta = delta.detach().requires_grad_(True)
+        cams = cams.detach().requires_grad_(True)
+        lbs_param.grad = None
+        W = deform.skinning_matrix(deform.get_lbs(lbs_param), L, solver=solver)
+        _, ndc = deform.deform_and_project(mean_v, W, delta, cams, offset_z=5.0)
+        mask, _, _, _ = F_.soft_silhouette(ndc, faces, 64)
+        per = loss_utils.mask_losses(mask, target)["l1"].view(3, 4)
+        total, _ = loss_utils.hypothesis_weighting(per)
+        total.backward()
+        return total.detach(), delta.grad, cams.grad, lbs_param.grad
+
+    d0, c0 = wl.delta.to(dev), wl.cams.to(dev)
+    cap = graphs.CapturedStep(step, (d0, c0))
+    d1, c1 = d0 * 0.5, c0.clone()
+    c1[:, 1:3] += 0.03
+    got = [t.clone() for t in cap(d1, c1)]
+    want = step(d1, c1)
+    assert torch.allclose(got[0], want[0], rtol=1e-5)
+    for g, w in zip(got[1:], want[1:]):
+        assert util.rel_err(g.cpu().numpy(), w.cpu().numpy()) < 1e-4          # atomics order differs between runs
+    got2 = cap(d0.cpu().pin_memory(), c0.cpu().pin_memory())   # pinned host inputs
+    assert torch.allclose(got2[0], step(d0, c0)[0], rtol=1e-5)
