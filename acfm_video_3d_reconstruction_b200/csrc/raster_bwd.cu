@@ -13,9 +13,14 @@ namespace {
 // nothing: both are dropped while the region's pixels are compacted into a shared list, so the fragment
 // tensors of ~87% of the pixels are never read.  A lane then owns one ACTIVE pixel and walks its K
 // fragments starting at a lane-dependent offset, so that neighbouring pixels (which see the same faces
-// at the same depth rank) touch different vertices at the same time: shared-memory float atomics are
-// CAS loops on sm_100 and this keeps them to ~1 iteration.  Gradients reach HBM as one atomicAdd per
-// touched (CTA, vertex, component) instead of PyTorch3D's 4-9 global atomics per fragment.
+// at the same depth rank) touch different vertices at the same time.  Shared-memory FLOAT atomics are CAS spin
+// loops on sm_100 (ATOMS.CAST.SPIN) while 32-bit INTEGER adds are native fire-and-forget ATOMS.ADD, so the silhouette
+// path accumulates in fixed point: a per-CTA power-of-two scale is derived from the largest |grad_mask| of the
+// region (every contribution with |q - p| <= kRmax is then bounded by 2^27), and each contribution is split into a
+// signed high part and a 12-bit low part added to two int32 accumulators — exact to 2^-27 of the bound, with room
+// for 2^19 additions, and independent of the order of the additions.  The rare contribution beyond the bound (a
+// face larger than kRmax on screen) goes straight to global memory as a float atomic.  Gradients reach HBM as one
+// atomicAdd per touched (CTA, vertex, component) instead of PyTorch3D's 4-9 global atomics per fragment.
 // ---------------------------------------------------------------------------------------------
 struct BwdParams {
   const float* ndc;
@@ -38,7 +43,7 @@ struct BwdSmem {
     int o = 32;
     off_verts = o; o += ((V * 12 + 16 + 15) / 16) * 16;
     off_faces = o; o += F * 8;
-    off_acc = o; o += ((V * 8 + 15) / 16) * 16;
+    off_acc = o; o += ((V * 16 + 15) / 16) * 16;  // (V,2) x {high, low} int32 (fixed point) or (V,2) float
     off_list = o; o += kRegion * kRegion * 2;
     total = o;
   }
@@ -57,24 +62,46 @@ __device__ __forceinline__ float seg_foot(float px, float py, float ax, float ay
   return dx * dx + dy * dy;
 }
 
+constexpr float kRmax = 0.25f;  // fixed-point bound on |q - p| (NDC): blur band 0.03, faces up to half a screen wide
+
+// accumulation policy of one CTA: fixed point (silhouette path) or float CAS (general path)
+struct AccFixed {
+  int* hi; int* lo; float scale; float* gout;  // gout: global fallback for out-of-range contributions
+  __device__ __forceinline__ void add(int i, float c, bool in_range) const {
+    if (in_range) {
+      const int v = __float2int_rn(c * scale);
+      atomicAdd(hi + i, v >> 12);
+      atomicAdd(lo + i, v & 4095);
+    } else {
+      atomicAdd(gout + (i >> 1) * 3 + (i & 1), c);
+    }
+  }
+};
+struct AccFloat {
+  float* acc;
+  __device__ __forceinline__ void add(int i, float c, bool) const { atomicAdd(acc + i, c); }
+};
+
 // gradient of one fragment's squared distance w.r.t. the two vertices of its closest edge (PointLineDistanceBackward,
-// SURVEY.md §9.6), accumulated into the CTA's (V,2) shared accumulator
+// SURVEY.md §9.6), accumulated into the CTA's (V,2) accumulator
+template <typename Acc>
 __device__ __forceinline__ void frag_grad(float px, float py, float x0, float y0, float x1, float y1, float x2, float y2, float g,
-                                          int i0, int i1, int i2, float* acc) {
+                                          int i0, int i1, int i2, const Acc& acc) {
   float t01, t02, t12, qx01, qy01, qx02, qy02, qx12, qy12;
   const float d01 = seg_foot(px, py, x0, y0, x1, y1, t01, qx01, qy01);
   const float d02 = seg_foot(px, py, x0, y0, x2, y2, t02, qx02, qy02);
   const float d12 = seg_foot(px, py, x1, y1, x2, y2, t12, qx12, qy12);
-  float t, qx, qy;
+  float t, qx, qy, dm;
   int ia, ib;
-  if (d01 <= d02 && d01 <= d12) { t = t01; qx = qx01; qy = qy01; ia = i0; ib = i1; }       // same order as the forward's min
-  else if (d02 <= d12) { t = t02; qx = qx02; qy = qy02; ia = i0; ib = i2; }
-  else { t = t12; qx = qx12; qy = qy12; ia = i1; ib = i2; }
+  if (d01 <= d02 && d01 <= d12) { t = t01; qx = qx01; qy = qy01; ia = i0; ib = i1; dm = d01; }       // same order as the forward's min
+  else if (d02 <= d12) { t = t02; qx = qx02; qy = qy02; ia = i0; ib = i2; dm = d02; }
+  else { t = t12; qx = qx12; qy = qy12; ia = i1; ib = i2; dm = d12; }
+  const bool in_range = dm <= kRmax * kRmax;
   const float gx = g * 2.0f * (qx - px), gy = g * 2.0f * (qy - py);
-  atomicAdd(acc + ia * 2, (1.0f - t) * gx);
-  atomicAdd(acc + ia * 2 + 1, (1.0f - t) * gy);
-  atomicAdd(acc + ib * 2, t * gx);
-  atomicAdd(acc + ib * 2 + 1, t * gy);
+  acc.add(ia * 2, (1.0f - t) * gx, in_range);
+  acc.add(ia * 2 + 1, (1.0f - t) * gy, in_range);
+  acc.add(ib * 2, t * gx, in_range);
+  acc.add(ib * 2 + 1, t * gy, in_range);
 }
 
 // FROM_MASK: the upstream gradient is d loss / d mask and the blend backward (§9.5) is fused in;
@@ -88,7 +115,10 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   int* nactive = reinterpret_cast<int*>(smem + 8);
   int* next_chunk = reinterpret_cast<int*>(smem + 12);
   ushort4* sfaces = reinterpret_cast<ushort4*>(smem + L.off_faces);
-  float* acc = reinterpret_cast<float*>(smem + L.off_acc);
+  float* accf = reinterpret_cast<float*>(smem + L.off_acc);
+  int* acc_hi = reinterpret_cast<int*>(smem + L.off_acc);
+  int* acc_lo = acc_hi + p.V * 2;
+  unsigned* gmax_bits = reinterpret_cast<unsigned*>(smem + 16);
   unsigned short* alist = reinterpret_cast<unsigned short*>(smem + L.off_list);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int regions = p.regions_x * p.regions_y;
@@ -97,17 +127,29 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
   const int K = p.K;
 
-  if (tid == 0) { *nactive = 0; *next_chunk = 0; }
+  if (tid == 0) { *nactive = 0; *next_chunk = 0; *gmax_bits = 0u; }
   __syncthreads();
   // ---- 1. compact the region's active pixels (coalesced reads of mask / grad_mask) -------------------
   for (int i0 = 0; i0 < kRegion * kRegion; i0 += NT) {
     const int i = i0 + tid;
     const int x = px0 + (i & (kRegion - 1)), y = py0 + (i / kRegion);
     bool act = false;
+    float gabs = 0.0f;
     if (x < p.W && y < p.H) {
       const long long pix = ((long long)n * p.H + y) * p.W + x;
-      if (FROM_MASK) act = (p.mask[pix] != 0.0f) && (p.grad_mask[pix] != 0.0f);
-      else act = p.p2f[pix * K] >= 0;
+      if (FROM_MASK) {
+        gabs = fabsf(p.grad_mask[pix]);
+        act = (p.mask[pix] != 0.0f) && (gabs != 0.0f) && (gabs <= 3.0e38f);  // NaN / inf upstream gradients are dropped
+        if (!act) gabs = 0.0f;
+      } else {
+        act = p.p2f[pix * K] >= 0;
+      }
+    }
+    if (FROM_MASK) {
+      gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, 16)); gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, 8));
+      gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, 4)); gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, 2));
+      gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, 1));
+      if (lane == 0 && gabs > 0.0f) atomicMax(gmax_bits, __float_as_uint(gabs));  // non-negative floats order like their bits
     }
     const unsigned m = __ballot_sync(0xffffffffu, act);
     int base = 0;
@@ -125,13 +167,24 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
     const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
     sfaces[f] = make_ushort4((unsigned short)fp[0], (unsigned short)fp[1], (unsigned short)fp[2], 0);
   }
-  for (int i = tid; i < p.V * 2; i += NT) acc[i] = 0.0f;
+  for (int i = tid; i < p.V * 4; i += NT) acc_hi[i] = 0;  // both int32 planes; as floats, 0.0f twice over
   __syncthreads();
   const float* sv = stage_bulk_1d(smem + L.off_verts, p.ndc + (size_t)n * p.V * 3, (uint32_t)p.V * 12u, bar, 0);
 
   // ---- 2. one active pixel per lane, 32 at a time, chunks pulled dynamically --------------------------
   const float inv_sigma = 1.0f / p.sigma;
   const float inv_w = 1.0f / (float)p.W, inv_h = 1.0f / (float)p.H;
+  float* gout = p.grad_ndc + (size_t)n * p.V * 3;
+  // |contribution| <= |grad_mask| / sigma * 2 |q - p| (alpha, prob, t <= 1)  =>  bound = gmax / sigma * 2 kRmax, rounded up
+  // to a power of two; scale maps the bound to 2^27
+  float fx_scale = 1.0f;
+  if (FROM_MASK) {
+    int e;
+    frexpf(__uint_as_float(*gmax_bits) * inv_sigma * (2.0f * kRmax), &e);  // bound < 2^e
+    fx_scale = ldexpf(1.0f, 27 - e);
+  }
+  const AccFixed accx{acc_hi, acc_lo, fx_scale, gout};
+  const AccFloat accl{accf};
   const int nchunks = (na + 31) / 32;
   const bool vec = (K & 3) == 0 && (((uintptr_t)p.p2f | (uintptr_t)p.dists | (FROM_MASK ? 0 : (uintptr_t)p.grad_dists)) & 15u) == 0;
   while (true) {
@@ -179,8 +232,8 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
           if (gd == 0.0f) continue;
           if (signbit(d)) gd = -gd;  // dist = inside ? -|d| : |d|
           const ushort4 iv = sfaces[(int)(fid[e] - nF)];
-          frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd,
-                    iv.x, iv.y, iv.z, acc);
+          if (FROM_MASK) frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accx);
+          else frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accl);
         }
       }
     } else {
@@ -196,15 +249,15 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
         if (gd == 0.0f) continue;
         if (signbit(d)) gd = -gd;
         const ushort4 iv = sfaces[f];
-        frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd,
-                  iv.x, iv.y, iv.z, acc);
+        if (FROM_MASK) frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accx);
+        else frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accl);
       }
     }
   }
   __syncthreads();
-  float* gout = p.grad_ndc + (size_t)n * p.V * 3;
+  const float inv_scale = 1.0f / fx_scale;
   for (int i = tid; i < p.V * 2; i += NT) {
-    const float a = acc[i];
+    const float a = FROM_MASK ? ((float)acc_hi[i] * 4096.0f + (float)acc_lo[i]) * inv_scale : accf[i];
     if (a != 0.0f) atomicAdd(gout + (i >> 1) * 3 + (i & 1), a);
   }
 }
