@@ -301,6 +301,8 @@ def run_ours(args):
             tj = json.load(open(traffic)).get(args.workload, {})
             out["roofline"]["traffic"] = tj.get("raster_fwd_kernel")
             out["roofline_bwd"]["traffic"] = tj.get("raster_soft_bwd_kernel")
+            if out["roofline_bwd"]["traffic"] and kb_avg:
+                out["roofline_bwd"]["frac_by_traffic"] = out["roofline_bwd"]["traffic"] / (kb_avg * 1e-3) / 1e9 / peak
         except Exception:
             pass
     if world == 1:
