@@ -170,8 +170,12 @@ class HotPath:
         total, _ = loss_utils.hypothesis_weighting(per)            # multiframe/main.py:735-746
         total.backward()
         if world > 1:
-            parallel.allreduce_shared_grads([self.lbs_param])      # shared-parameter gradient
+            self.allreduce()
         return total.detach(), delta.grad, cams.grad
+
+    def allreduce(self):
+        from acfm_video_3d_reconstruction_b200 import parallel
+        parallel.allreduce_shared_grads([self.lbs_param])          # shared-parameter gradient
 
 
 def run_ours(args):
@@ -233,17 +237,25 @@ def run_ours(args):
     # The caller reads the loss every step, so the ~80 host-side launches of a step would sit on the critical path after each
     # synchronisation: the step is captured in a CUDA graph once (graphs.CapturedStep) and replayed; every step copies its
     # inputs from pinned host memory into the graph's static buffers and copies loss + gradients back, inside the timed region.
-    e2e_mode = "cuda graph replay"
+    e2e_mode = "cuda graph replay" + (" + NCCL all-reduce of the shared-parameter gradient after each replay" if world > 1 else "")
     step_fn = None
-    if world == 1:
-        try:
-            from acfm_video_3d_reconstruction_b200 import graphs
-            step_fn = graphs.CapturedStep(lambda d_, c_, t_, e_: hp.step(d_, c_, t_, e_, world=1), dev_in)
-        except Exception as exc:  # capture is an optimisation, not a requirement
-            e2e_mode = f"eager launches (graph capture failed: {type(exc).__name__})"
-            step_fn = None
-    else:
-        e2e_mode = "eager launches (NCCL all-reduce inside the step)"
+    try:
+        from acfm_video_3d_reconstruction_b200 import graphs
+        captured = graphs.CapturedStep(lambda d_, c_, t_, e_: hp.step(d_, c_, t_, e_, world=1), dev_in)
+
+        def step_fn(*host):
+            out = captured(*host)
+            if world > 1:
+                hp.allreduce()                                      # lbs_param.grad lives in the graph's static memory
+            return out
+    except Exception as exc:  # capture is an optimisation, not a requirement
+        e2e_mode = f"eager launches (graph capture failed: {type(exc).__name__})"
+        step_fn = None
+    if world > 1:   # all ranks must take the same path (the collective count per step must match)
+        ok = torch.tensor([1.0 if step_fn is not None else 0.0], device=device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            step_fn, e2e_mode = None, "eager launches (graph capture failed on a rank)"
     if step_fn is None:
         def step_fn(*host):
             return hp.step(*[h.to(device, non_blocking=True) for h in host], world=world)
@@ -469,7 +481,8 @@ def run_reference(args):
     orc.build()
     cfg = WORKLOADS[args.workload]
     wl = synthetic.Workload(cfg["template"], cfg["frames"], cfg["G"], cfg["handles"], cfg["img"], seed=0, offset_z=cfg["offset_z"])
-    threads = orc.max_threads()
+    # rank 0 runs alone and may use every host core (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)
+    threads = max(orc.max_threads(), os.cpu_count() or 1)
     torch.set_num_threads(threads)
     G = cfg["G"]
     nf = max(1, min(cfg["frames"], max(1, threads // G) if cfg["img"] <= 256 else 1))
