@@ -201,3 +201,36 @@ def test_record_capacity_and_cta_shapes(cap, warps, monkeypatch):
     ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
     out = _gpu_mask_render(X, faces, cam, S, 5.0)
     _assert_fragments_equal(out, ref)
+
+
+@pytest.mark.parametrize("scale,blur,K", [(0.05, 1e-3, 3), (0.5, 0.0, 8), (0.5, 0.05, 8), (5.0, 1e-3, 4), (500.0, 1e-2, 6), (0.5, 1e-3, 64)])
+def test_triangle_soups_forward_and_backward(scale, blur, K):
+    """Random triangle soups — overlapping, sliver, off-screen, behind-the-camera and screen-filling faces (coordinates up to
+    ~1e3 NDC): the conservative culling margins of the forward and the out-of-range (global atomic) branch of the fixed-point
+    backward must hold for arbitrary inputs, not just for the templates."""
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    gen = torch.Generator().manual_seed(int(scale * 1000) + K)
+    N, F, S = 5, 40, 48
+    V = 3 * F
+    xy = scale * torch.randn(N, V, 2, generator=gen)
+    xy[:, ::7] *= 0.02                                   # some slivers / tiny faces
+    z = torch.rand(N, V, 1, generator=gen) * 2.5 + 0.5
+    z[:, ::11] -= 2.0                                    # some vertices behind the camera
+    ndc = torch.cat([xy, z], -1).numpy().astype(np.float32)
+    faces = np.repeat(np.arange(V, dtype=np.int64).reshape(1, F, 3), N, 0)
+    ref = orc.rasterize(ndc, faces, S, blur, K, want_bary=False)
+    nd = torch.from_numpy(ndc).cuda().requires_grad_(True)
+    if blur > 0:
+        mask, p2f, zb, d = F_.soft_silhouette(nd, torch.from_numpy(faces).cuda(), S, blur, K, 1e-2)
+        out = dict(pix_to_face=p2f, zbuf=zb, dists=d)
+    else:
+        out = F_.rasterize(nd.detach(), torch.from_numpy(faces).cuda(), S, blur, K)
+    _assert_fragments_equal(out, ref)
+    assert (ref["pix_to_face"] >= 0).mean() > 0.01
+    if blur > 0:
+        ref["ndc"] = ndc
+        gm = torch.randn(N, S, S, generator=gen).numpy().astype(np.float32)
+        gd = orc.sigmoid_alpha_blend_backward(ref["dists"], ref["pix_to_face"], gm, 1e-2)
+        g_ref = orc.scatter_face_grads(orc.rasterize_backward(ref["face_verts"], ref["pix_to_face"], grad_dists=gd), faces, V)
+        (mask * torch.from_numpy(gm).cuda()).sum().backward()
+        assert util.rel_err(nd.grad.cpu().numpy(), g_ref) < 1e-3
