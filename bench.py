@@ -320,6 +320,8 @@ def run_ours(args):
     if world == 1:
         out["target_maps"] = target_maps_bench(hp, cfg, peak, cpu=not args.no_cpu_baseline)
         out["post_optimize"] = post_optimize_bench(hp, cfg, cpu=not args.no_cpu_baseline)
+        if not args.no_cpu_baseline:
+            out["gpu_standin"] = gpu_standin_bench(hp, cfg)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(cfg, hp.wl, hp.h_target, hp.h_edt, max_seconds=20.0)
     print(json.dumps(out), flush=True)
@@ -362,6 +364,35 @@ def target_maps_bench(hp, cfg, peak, cpu=True, iters=10):
         out["cpu_baseline"] = {"value": len(mn) / dt, "unit": "masks/s", "cores": 1, "kind": "port",
                                "sample": f"{len(mn)} masks, scipy.ndimage EDT x3 + restated find_boundaries, serial as in set_input"}
     return out
+
+
+def gpu_standin_bench(hp, cfg, renders=4):
+    """Side measurement: BASELINE.md's B-GPU-torch — a dense pure-PyTorch soft rasterizer (oracle/torch_dense.py, checked against
+    the C oracle in tests) on this same GPU, fwd + autograd bwd, on a bounded sample of the workload's renders.  A STAND-IN for
+    "PyTorch3D's CUDA path", which is not installable here; it does O(pixels x faces) work, PyTorch3D bins faces."""
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    from oracle import torch_dense
+    with torch.no_grad():
+        X = hp.mean_v[None].repeat(renders, 1, 1)
+        ndc = F_.project(X, hp.h_cams[:renders].to(hp.device), cfg["offset_z"], -1.0, -1.0, F_.EYE_Z)
+    gm = torch.randn(renders, cfg["img"], cfg["img"], device=hp.device)
+
+    def one(k):
+        nd = ndc[k:k + 1].clone().requires_grad_(True)
+        mask, _ = torch_dense.soft_silhouette(nd, hp.faces[0], cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
+        (mask * gm[k:k + 1]).sum().backward()
+
+    one(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(renders):
+        one(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": renders / (ms * 1e-3), "unit": "renders/s", "kind": "stand-in (dense pure-PyTorch rasterizer, raster fwd+bwd only)",
+            "sample": f"{renders} renders of the workload, one at a time (each keeps ~10 GB of (pixels x faces) temporaries for autograd)"}
 
 
 def post_optimize_bench(hp, cfg, cpu=True, frames=12, iters=20):

@@ -234,3 +234,22 @@ def test_triangle_soups_forward_and_backward(scale, blur, K):
         g_ref = orc.scatter_face_grads(orc.rasterize_backward(ref["face_verts"], ref["pix_to_face"], grad_dists=gd), faces, V)
         (mask * torch.from_numpy(gm).cuda()).sum().backward()
         assert util.rel_err(nd.grad.cpu().numpy(), g_ref) < 1e-3
+
+
+def test_torch_dense_standin_matches_oracle():
+    """The pure-PyTorch dense renderer bench.py times as the "PyTorch3D CUDA path" stand-in (BASELINE.md B-GPU-torch) computes
+    the same silhouettes and gradients as the C oracle (fragments may differ at ties: it is not bit-exact by construction)."""
+    from oracle import torch_dense
+    v, f = util.template("bird")
+    N, S = 2, 64
+    X, cam = util.synth_verts(v, N, seed=41), util.synth_cams(N, seed=42)
+    faces = np.repeat(f[None], N, 0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
+    gm = np.random.default_rng(3).standard_normal((N, S, S)).astype(np.float32)
+    g_ref = orc.neural_renderer_mask_backward(ref, faces, gm)
+    nd = torch.from_numpy(ref["ndc"]).cuda().requires_grad_(True)
+    mask, p2f = torch_dense.soft_silhouette(nd, torch.from_numpy(f).cuda(), S, orc.BLUR_SOFT, orc.K_SOFT, orc.SIGMA)
+    assert np.abs(mask.detach().cpu().numpy() - ref["mask"]).max() < 1e-4
+    assert (p2f.cpu().numpy() != ref["pix_to_face"]).mean() < 1e-3
+    (mask * torch.from_numpy(gm).cuda()).sum().backward()
+    assert util.rel_err(nd.grad.cpu().numpy(), g_ref) < 1e-3
