@@ -301,11 +301,19 @@ __device__ __forceinline__ void list_insert(unsigned long long* lk, float* ld, i
     if (key > last) return;  // not nearer than the current K-th
     pos = K - 1;
   }
+  // Two elements per shared-memory round trip: the second pair of loads is speculative.  The shift loop is a chain of
+  // dependent LDS -> compare -> STS and the warp waits for its longest shift, so latency per element is what counts
+  // (measured at C2: 1 element per trip 4.17 ms, 2 per trip 3.89 ms, 3 and 4 per trip 4.12 / 4.16 ms).
   while (pos > 0) {
-    const unsigned long long kp = lk[pos - 1];
-    const float dp = ld[pos - 1];
-    if (kp < key) break;
-    lk[pos] = kp; ld[pos] = dp;
+    const unsigned long long k1 = lk[pos - 1];
+    const float d1 = ld[pos - 1];
+    const unsigned long long k2 = pos > 1 ? lk[pos - 2] : 0ull;
+    const float d2 = pos > 1 ? ld[pos - 2] : 0.0f;
+    if (k1 < key) break;
+    lk[pos] = k1; ld[pos] = d1;
+    --pos;
+    if (pos == 0 || k2 < key) break;
+    lk[pos] = k2; ld[pos] = d2;
     --pos;
   }
   lk[pos] = key; ld[pos] = sd;
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
         if (cand) queue[(qn++) * 32 + lane] = (unsigned char)jj;
         full = __any_sync(0xffffffffu, qn == kQueue);
       }
-      // (c) evaluate: each lane pops its own queue
+      // (c) evaluate: each lane pops its own queue (prefetching the next entry's record a round early measured no gain)
       const int qmax = __reduce_max_sync(0xffffffffu, qn);
       for (int i = 0; i < qmax; ++i) {
         if (i < qn) {
