@@ -73,6 +73,7 @@ class OF_NeuralRenderer(torch.nn.Module):
     def forward(self, verts, faces):
         with torch.no_grad():
             # R = diag(-1,1,1), T = (0,0,2.732): exact sign flip, one rounding on z
-            ndc = verts * verts.new_tensor([-1.0, 1.0, 1.0]) + verts.new_tensor([0.0, 0.0, F_.EYE_Z])
+            # no host-side constants here (keeps the call CUDA-graph capturable)
+            ndc = torch.stack([-verts[..., 0], verts[..., 1], verts[..., 2] + F_.EYE_Z], dim=-1)
             fr = F_.rasterize(ndc, faces, self.img_size, 0.0, 1)
         return fr["pix_to_face"]

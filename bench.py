@@ -35,6 +35,9 @@ WORKLOADS = {
     # name: (template, frames/rank, G, handles, img, K, offset_z)
     "C2": dict(template="bird", frames=64, G=8, handles=32, img=256, K=20, offset_z=5.0,
                desc="C2 monocular bird step: 642v/1280f, batch 64 x 8 camera hypotheses = 512 renders/GPU, 256x256, K=20, 32 handles"),
+    "C3": dict(template="horse", frames=64, G=8, handles=16, img=256, K=20, offset_z=0.0, full=True, clip_frames=16,
+               desc="C3 multiframe quadruped step, one GPU's share: 4 clips x 16 frames x 8 cameras = 512 renders/GPU, 256x256, K=20, "
+                    "16 handles; full loss set (camera assembly, mask l1 + edt, boundary, optical-flow, keypoint, hypothesis weighting)"),
     "C4": dict(template="ico4", frames=4, G=2, handles=32, img=512, K=50, offset_z=0.0,
                desc="C4 high-res stress: 2562v/5120f icosphere, 8 renders/GPU, 512x512, K=50"),
 }
@@ -128,6 +131,31 @@ class HotPath:
         self.h_loss = torch.empty((), dtype=torch.float32).pin_memory()
         self.h_gdelta = torch.empty_like(wl.delta).pin_memory()
         self.h_gcams = torch.empty_like(wl.cams).pin_memory()
+        if cfg.get("full"):
+            self._full_inputs(rank)
+
+    def _full_inputs(self, rank):
+        """Device-resident synthetic targets of the full multiframe loss set: boundary points of the target
+        masks (our GPU compute_boundaries), noisy projected keypoints, masked random flow, mirror / affine augmentation flags."""
+        from acfm_video_3d_reconstruction_b200 import image_utils
+        cfg, d = self.cfg, self.device
+        gen = torch.Generator().manual_seed(100 + rank)
+        NB, T = cfg["frames"], cfg["clip_frames"]
+        tgt = self.h_target.to(d)
+        self.boundaries = image_utils.compute_boundaries(tgt)
+        self.bds_sel = torch.randperm(self.boundaries.shape[1], generator=gen)[:1000].to(d)
+        Kp = 16
+        self.vert2kp = torch.randn(Kp, self.wl.V, generator=gen).mul(4.0).to(d).requires_grad_(True)
+        kp_xy = torch.rand(NB, Kp, 2, generator=gen) * 1.2 - 0.6
+        self.kps = torch.cat([kp_xy, (torch.rand(NB, Kp, 1, generator=gen) > 0.2).float()], -1).to(d)
+        flows = 2.0 * torch.randn(NB // T, T, cfg["img"], cfg["img"], 2, generator=gen)
+        self.flows = flows.to(d) * tgt.reshape(NB // T, T, cfg["img"], cfg["img"], 1)
+        self.mirror = (torch.rand(NB, generator=gen) > 0.5).float().to(d)
+        tr = torch.cat([torch.rand(NB, 1, generator=gen) * 0.2 + 0.9, torch.rand(NB, 2, generator=gen) * 0.1 - 0.05,
+                        (torch.rand(NB, 1, generator=gen) > 0.5).float()], 1)
+        self.transforms = tr.to(d)
+        from acfm_video_3d_reconstruction_b200 import OF_NeuralRenderer
+        self.of_renderer = OF_NeuralRenderer(cfg["img"])
 
     def _targets(self, rank):
         """mask_gt = our own render of an independently drawn pose, thresholded; edt = scipy EDT of it (setup only)."""
@@ -163,11 +191,27 @@ class HotPath:
         self.lbs_param.grad = None
         lbs = deform.get_lbs(self.lbs_param)                       # MeshNet.get_lbs: softmax over vertices
         W = deform.skinning_matrix(lbs, self.L, solver=self.solver)
-        _, ndc = deform.deform_and_project(self.mean_v, W, delta, cams, offset_z=cfg["offset_z"])
+        full = cfg.get("full", False)
+        cam_pred = cams
+        if full:   # `cams` are the raw per-frame camera embeddings: multiframe/main.py:573-582
+            from acfm_video_3d_reconstruction_b200 import camera
+            cam_pred = camera.assemble_cameras(cams, self.mirror, self.transforms, 0.05)
+        pred_v, ndc = deform.deform_and_project(self.mean_v, W, delta, cam_pred, offset_z=cfg["offset_z"])
         mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
         ls = loss_utils.mask_losses(mask, target, edt)
-        per = (ls["l1"] + W_EDT * ls["edt"]).view(cfg["G"], cfg["frames"])
-        total, _ = loss_utils.hypothesis_weighting(per)            # multiframe/main.py:735-746
+        per = ls["l1"] + W_EDT * ls["edt"]
+        if full:
+            G, NB, T = cfg["G"], cfg["frames"], cfg["clip_frames"]
+            self.vert2kp.grad = None
+            pred_proj = F_.project(pred_v, cam_pred, 0.0)          # renderer.project_points (main.py:715), xy used in place
+            per = per + W_EDT * loss_utils.bds_loss(pred_proj, self.boundaries, self.faces, p2f, reduce=False, indices=self.bds_sel)
+            kp_verts = torch.softmax(self.vert2kp, dim=1).matmul(pred_v)                       # main.py:691-692
+            per = per + loss_utils.kp_l2_loss(F_.project(kp_verts, cam_pred, 0.0), self.kps, reduction='none')
+            of = loss_utils.optical_flow_loss(pred_v.repeat(G, 1, 1).reshape(G * NB // T, T, -1, 3),
+                                              self.faces.expand(G * NB, -1, -1).reshape(G * NB // T, T, -1, 3), cam_pred, self.flows,
+                                              self.of_renderer, None, reduce=False)[0]         # (G*B, T-1)
+            per = per + 0.1 * of.mean(1).repeat_interleave(T)
+        total, _ = loss_utils.hypothesis_weighting(per.view(cfg["G"], cfg["frames"]))          # multiframe/main.py:735-746
         total.backward()
         if world > 1:
             self.allreduce()
