@@ -26,7 +26,8 @@ SIGNATURES = {
     "acfm_softmax_cols_fwd": [_c_vp, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_softmax_cols_bwd": [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_raster_fwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int,
-                        _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
+                        _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+    "acfm_raster_fwd_workspace_bytes": [_c_int, _c_int, _c_int],
     "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_dists_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,
@@ -77,7 +78,8 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == "acfm_last_error_string" else ctypes.c_int
+            fn.restype = (ctypes.c_char_p if name == "acfm_last_error_string" else
+                          ctypes.c_int64 if name == "acfm_raster_fwd_workspace_bytes" else ctypes.c_int)
         _lib = l
     return _lib
 

@@ -40,6 +40,8 @@
 //
 // HBM-bound on the API-mandated (N,H,W,K) fragment tensors: 16K+4 bytes written per pixel.
 #include "common.cuh"
+#include <algorithm>
+
 #include "raster_common.cuh"
 
 namespace {
@@ -62,6 +64,7 @@ struct RasterParams {
   int regions_x, regions_y;
   int cap;      // face records per region
   int vec_ok;   // output pointers are 16-byte aligned
+  const int* work;  // split path: {countR, countF, -, -, listR[N*regions], listF[N*regions][2]} written by raster_prep_kernel
 };
 
 // shared-memory carve-up, identical on host and device
@@ -321,7 +324,7 @@ __device__ __forceinline__ void list_insert(unsigned long long* lk, float* ld, i
 }
 
 template <int NWARPS, typename IdxT>
-__global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterParams p) {
+__global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 96) raster_fwd_kernel(const RasterParams p) {
   constexpr int NT = NWARPS * 32;
   extern __shared__ __align__(16) unsigned char smem[];
   const FwdSmem L(p.V, p.F, p.K, NWARPS, p.cap);
@@ -339,8 +342,13 @@ __global__ void __launch_bounds__(NWARPS * 32) raster_fwd_kernel(const RasterPar
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int regions = p.regions_x * p.regions_y;
-  const int n = blockIdx.x / regions;
-  const int rg = blockIdx.x - n * regions;
+  int unit = blockIdx.x;
+  if (p.work) {  // split path: only regions the mesh can touch reach this kernel (the others go to raster_fill_kernel)
+    if (unit >= p.work[0]) return;
+    unit = p.work[4 + unit];
+  }
+  const int n = unit / regions;
+  const int rg = unit - n * regions;
   const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
   const int px1 = min(px0 + kRegion, p.W), py1 = min(py0 + kRegion, p.H);
   const int K = p.K;
@@ -739,6 +747,168 @@ int launch_fwd(const RasterParams& p, int smem, int ctas, cudaStream_t st) {
   return ACFM_OK;
 }
 
+
+// ---- split path: region classification + concurrent fill -----------------------------------------------
+// At the reference's workloads ~75% of the (render, region) units lie outside the blur-expanded bounding box of the mesh
+// and 87% of all fragment bytes are -1 padding.  Inside the rasterizer kernel those units hold a 109 KB / 256-thread CTA
+// slot while their stores drain (18% of the kernel's warp samples, profiles/raster_fwd_r01.md), slots the issue-bound
+// units then lack.  The split path classifies the units first (raster_prep_kernel, one small CTA per render), gives the
+// rasterizer kernel only the units the mesh can touch, and pads the others from raster_fill_kernel on a second stream:
+// one-warp CTAs with a few KB of shared memory, which run in the resources the rasterizer leaves free, so the HBM write
+// stream overlaps the arithmetic (C2: 3.97 -> 3.17 ms; the rasterizer alone 3.08 ms, the fill alone 1.33 ms).
+constexpr int kPrepThreads = 128;
+
+__global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterParams p, int* ws) {
+  __shared__ float red[kPrepThreads / 32][4];
+  __shared__ float box[4];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* v = p.ndc + (size_t)n * p.V * 3;
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (int i = tid; i < p.V; i += kPrepThreads) {
+    const float x = v[i * 3], y = v[i * 3 + 1];
+    xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  if (lane == 0) { red[warp][0] = xmin; red[warp][1] = xmax; red[warp][2] = ymin; red[warp][3] = ymax; }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 1; w < kPrepThreads / 32; ++w) {
+      xmin = fminf(xmin, red[w][0]); xmax = fmaxf(xmax, red[w][1]); ymin = fminf(ymin, red[w][2]); ymax = fmaxf(ymax, red[w][3]);
+    }
+    // the same expansion as the per-face bounding boxes, so the classification is exact
+    box[0] = fsub(xmin, p.sq_blur); box[1] = fadd(xmax, p.sq_blur); box[2] = fsub(ymin, p.sq_blur); box[3] = fadd(ymax, p.sq_blur);
+  }
+  __syncthreads();
+  const float bxmin = box[0], bxmax = box[1], bymin = box[2], bymax = box[3];
+  const int regions = p.regions_x * p.regions_y;
+  int* listR = ws + 4;
+  int* listF = ws + 4 + p.N * regions;
+  for (int r0 = 0; r0 < regions; r0 += kPrepThreads) {
+    const int rg = r0 + tid;
+    bool live = false, inr = rg < regions;
+    if (inr) {
+      const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
+      const int px1 = min(px0 + kRegion, p.W), py1 = min(py0 + kRegion, p.H);
+      const float r_xhi = pix_to_ndc(p.W - 1 - px0, p.W), r_xlo = pix_to_ndc(p.W - 1 - (px1 - 1), p.W);
+      const float r_yhi = pix_to_ndc(p.H - 1 - py0, p.H), r_ylo = pix_to_ndc(p.H - 1 - (py1 - 1), p.H);
+      live = p.F > 0 && !((r_xlo > bxmax) || (r_xhi < bxmin) || (r_ylo > bymax) || (r_yhi < bymin));
+    }
+    // units for the rasterizer: one per live region; units for the fill kernel: horizontal RUNS of empty regions inside one
+    // row of regions (and one warp's 32 consecutive regions), so that a bulk store can span the whole run
+    const unsigned mr = __ballot_sync(0xffffffffu, inr && live), me = __ballot_sync(0xffffffffu, inr && !live);
+    const int col = inr ? rg % p.regions_x : 0;
+    const bool start = inr && !live && (lane == 0 || col == 0 || !((me >> (lane - 1)) & 1u));
+    int run = 0;
+    if (start) {
+      const unsigned stop = ~(me >> lane);  // lowest set bit = first non-empty region at or after this lane
+      run = min(stop ? __ffs(stop) - 1 : 32, p.regions_x - col);
+    }
+    const unsigned mf = __ballot_sync(0xffffffffu, start);
+    int br = 0, bf = 0;
+    if (lane == 0) {
+      if (mr) br = atomicAdd(&ws[0], __popc(mr));
+      if (mf) bf = atomicAdd(&ws[1], __popc(mf));
+    }
+    br = __shfl_sync(0xffffffffu, br, 0); bf = __shfl_sync(0xffffffffu, bf, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (inr && live) listR[br + __popc(mr & lt)] = n * regions + rg;
+    if (start) {
+      const int e = bf + __popc(mf & lt);
+      listF[2 * e] = n * regions + rg;
+      listF[2 * e + 1] = run;
+    }
+  }
+}
+
+// The padding is written by the TMA unit (cp.async.bulk shared -> global) from a constant pattern in shared memory: a CTA
+// of ordinary stores saturates its SM's LSU / MIO queue, which the co-resident rasterizer CTAs need for their K-list
+// traffic (measured: LSU fill beside the rasterizer 4.05-4.23 ms, no better than the single kernel); a bulk store is one
+// instruction per row piece and leaves the LSU alone.  One warp per CTA, lane = pixel row of the run.  The pattern holds
+// max(32 K, 640) fragment slots (7.5 KB up to K = 20), so one such CTA fits beside two resident rasterizer CTAs; measured
+// at C2, 5 KB / 2.5 KB pieces reach the HBM write rate with one CTA per SM, 2 KB / 1 KB pieces only a third of it.
+constexpr int kFillThreads = 32;
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void bulk_fill_row(void* dst, const void* pat_smem, int slots, int slot_bytes, int chunk) {
+  for (int o = 0; o < slots; o += chunk)
+    bulk_s2g(reinterpret_cast<unsigned char*>(dst) + (size_t)o * slot_bytes, pat_smem, (uint32_t)(min(chunk, slots - o) * slot_bytes));
+}
+
+__host__ __device__ inline int fill_pattern_slots(int K) { return max(kRegion * K, 640); }
+
+__global__ void __launch_bounds__(kFillThreads) raster_fill_kernel(const RasterParams p, const int* ws, int bulk_ok) {
+  extern __shared__ __align__(128) unsigned char pat[];
+  const int regions = p.regions_x * p.regions_y;
+  const int countF = ws[1];
+  const int* listF = ws + 4 + p.N * regions;
+  const int lane = threadIdx.x;
+  const int K = p.K, chunk = fill_pattern_slots(K);
+  long long* pat8 = reinterpret_cast<long long*>(pat);                         // [chunk] int64 -1
+  float* pat4 = reinterpret_cast<float*>(pat + (size_t)chunk * 8);             // [chunk] float -1
+  if (bulk_ok) {
+    for (int e = lane; e < chunk; e += kFillThreads) { pat8[e] = -1ll; pat4[e] = -1.0f; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
+    __syncwarp();
+  }
+  for (int w = blockIdx.x; w < countF; w += gridDim.x) {
+    const int unit = listF[2 * w], run = listF[2 * w + 1];
+    const int n = unit / regions, rg = unit - n * regions;
+    const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
+    const int px1 = min(px0 + run * kRegion, p.W), py1 = min(py0 + kRegion, p.H);
+    const int npx = px1 - px0, row_el = npx * K;
+    if (bulk_ok && (row_el & 3) == 0) {
+      if (py0 + lane < py1) {
+        const long long g = (((long long)n * p.H + py0 + lane) * p.W + px0) * K;  // first fragment slot of the row
+        bulk_fill_row(p.p2f + g, pat8, row_el, 8, chunk);
+        bulk_fill_row(p.zbuf + g, pat4, row_el, 4, chunk);
+        bulk_fill_row(p.dists + g, pat4, row_el, 4, chunk);
+        if (p.bary) bulk_fill_row(p.bary + g * 3, pat4, row_el * 3, 4, chunk);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (p.mask)
+        for (int y = py0; y < py1; ++y)
+          for (int x = lane; x < npx; x += kFillThreads) p.mask[((long long)n * p.H + y) * p.W + px0 + x] = 0.0f;
+    } else {
+      cta_fill_rect<1>(p, n, px0, px1, py0, py1, 0, lane);
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the pattern must outlive the reads; writes complete before exit
+}
+
+// per-thread, per-device side stream + fork/join events of the split path
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int sms = 0;
+};
+int fork_join(ForkJoin** out) {
+  static thread_local ForkJoin fj[kAcfmMaxDevices];
+  int dev = 0;
+  ACFM_CUDA_OK(cudaGetDevice(&dev));
+  ForkJoin& f = fj[dev & (kAcfmMaxDevices - 1)];
+  if (!f.side) {
+    ACFM_CUDA_OK(cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev));
+    ACFM_CUDA_OK(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+    ACFM_CUDA_OK(cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming));
+    int lo = 0, hi = 0;
+    ACFM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // highest priority: the fill kernel's few CTAs (one per SM) must be dispatched BEFORE the rasterizer's grid — the block
+    // scheduler does not start a kernel while an earlier one of the same priority still has CTAs waiting
+    ACFM_CUDA_OK(cudaStreamCreateWithPriority(&f.side, cudaStreamNonBlocking, hi));
+  }
+  *out = &f;
+  return ACFM_OK;
+}
+
 // test / tuning hook: ACFM_FWD_WARPS and ACFM_FWD_CAP override the automatic choice
 int fwd_config(int V, int F, int K, int* smem, int* cap) {
   int nw = fwd_pick_config(V, F, K, smem, cap);
@@ -771,7 +941,7 @@ extern "C" int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, in
 extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N,
                                int V, int F, int H, int W, int K, float blur_radius, int clip_bary, int cull_backfaces,
                                float sigma, int64_t* pix_to_face, float* zbuf, float* dists, float* bary, float* mask,
-                               void* stream) {
+                               void* workspace, int64_t workspace_bytes, void* stream) {
   ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: bad sizes N=%d V=%d F=%d H=%d W=%d", N, V, F, H, W);
   ACFM_REQUIRE(K >= 1, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: faces_per_pixel K=%d must be >= 1", K);
   ACFM_REQUIRE(K <= 64, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: faces_per_pixel K=%d > 64 is not supported", K);
@@ -794,18 +964,55 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   const int nw = fwd_config(V, F, K, &smem, &cap);
   ACFM_REQUIRE(nw > 0, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: needs more than 232448 B of shared memory for V=%d F=%d K=%d", V, F, K);
   p.cap = cap;
+  p.work = nullptr;
   const long long ctas = (long long)N * p.regions_x * p.regions_y;
-  ACFM_REQUIRE(ctas < (1ll << 31), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: too many CTAs");
+  ACFM_REQUIRE(ctas < (1ll << 28), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: too many CTAs");
   cudaStream_t st = (cudaStream_t)stream;
+  // split path (see raster_prep_kernel): needs the caller's scratch; without it everything runs in the one kernel
+  static const bool no_split = getenv("ACFM_FWD_NOSPLIT") != nullptr;
+  static const char* only = getenv("ACFM_FWD_ONLY");  // timing hook: "raster" / "fill" launches just that half (wrong outputs)
+  ForkJoin* fj = nullptr;
+  if (workspace && !no_split) {
+    ACFM_REQUIRE(workspace_bytes >= 16 + 12 * ctas && (((uintptr_t)workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
+                 "acfm_raster_fwd: workspace must be 16-byte aligned and hold acfm_raster_fwd_workspace_bytes() = %lld bytes",
+                 16 + 12 * ctas);
+    if (fork_join(&fj) != ACFM_OK) return ACFM_ERR_CUDA;
+    int* ws = (int*)workspace;
+    ACFM_CUDA_OK(cudaMemsetAsync(ws, 0, 16, st));
+    raster_prep_kernel<<<N, kPrepThreads, 0, st>>>(p, ws);
+    ACFM_LAUNCH_OK("raster_prep_kernel");
+    p.work = ws;
+    ACFM_CUDA_OK(cudaEventRecord(fj->fork, st));
+    ACFM_CUDA_OK(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+    static const int fill_per_sm = getenv("ACFM_FILL_PER_SM") ? std::max(1, atoi(getenv("ACFM_FILL_PER_SM"))) : 1;
+    static const int fill_abs = getenv("ACFM_FILL_CTAS") ? atoi(getenv("ACFM_FILL_CTAS")) : 0;
+    const int fill_ctas = fill_abs > 0 ? fill_abs : (int)std::min<long long>(ctas, (long long)fj->sms * fill_per_sm / 2);
+    // bulk stores need 16-byte aligned rows: aligned bases, W*K (and so every row start) a multiple of 4 fragment slots
+    const int bulk_ok = p.vec_ok && (((long long)W * K) & 3) == 0 && (!bary || (((uintptr_t)bary) & 15u) == 0) &&
+                        getenv("ACFM_FILL_LSU") == nullptr;
+    if (!only || only[0] != 'r') raster_fill_kernel<<<fill_ctas, kFillThreads, fill_pattern_slots(K) * 12, fj->side>>>(p, ws, bulk_ok);
+    ACFM_LAUNCH_OK("raster_fill_kernel");
+    ACFM_CUDA_OK(cudaEventRecord(fj->join, fj->side));
+  }
+  int rc = ACFM_ERR_UNSUPPORTED;
 #define ACFM_FWD_CASE(NW)                                                                                       \
   case NW:                                                                                                      \
-    return faces_i64 ? launch_fwd<NW, long long>(p, smem, (int)ctas, st) : launch_fwd<NW, int>(p, smem, (int)ctas, st)
-  switch (nw) {
+    rc = faces_i64 ? launch_fwd<NW, long long>(p, smem, (int)ctas, st) : launch_fwd<NW, int>(p, smem, (int)ctas, st); \
+    break
+  switch ((fj && only && only[0] == 'f') ? -1 : nw) {
+    case -1: rc = ACFM_OK; break;
     ACFM_FWD_CASE(12);
     ACFM_FWD_CASE(10);
     ACFM_FWD_CASE(8);
     ACFM_FWD_CASE(4);
   }
 #undef ACFM_FWD_CASE
-  ACFM_REQUIRE(false, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: no launch configuration");
+  if (fj) ACFM_CUDA_OK(cudaStreamWaitEvent(st, fj->join, 0));  // join even after a failed launch: the side stream must not dangle
+  ACFM_REQUIRE(rc != ACFM_ERR_UNSUPPORTED, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: no launch configuration");
+  return rc;
+}
+
+extern "C" int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  return 16 + 12 * (int64_t)N * ((W + kRegion - 1) / kRegion) * ((H + kRegion - 1) / kRegion);
 }

@@ -6,6 +6,7 @@ allocated with torch's caching allocator so autograd / DataParallel gather keep 
 (SURVEY.md §8b "Ownership").
 """
 import math
+import os
 
 import torch
 
@@ -86,6 +87,10 @@ def project(verts, cams, offset_z=0.0, sx=1.0, sy=1.0, z_add=0.0):
 # -------------------------------------------------------------------------------------------------
 # rasterization
 # -------------------------------------------------------------------------------------------------
+# True: acfm_raster_fwd gets a scratch buffer and runs its split path (region classification + rasterizer + concurrent fill
+# kernel, see include/acfm_b200.h); False: the single-kernel path.  Same results; a switch for tests and A/B timing.
+SPLIT_FILL = os.environ.get("ACFM_SPLIT_FILL", "1") != "0"
+
 def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycentric_coords=False,
               cull_backfaces=False, sigma=0.0, want_bary=False, want_mask=False):
     """rasterize_meshes on screen-space verts (no autograd).  Returns dict of pix_to_face / zbuf / dists
@@ -102,15 +107,18 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
     dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
     bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if want_bary else None
     mask = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_mask else None
+    # scratch of the split path (region work lists): the empty regions are padded by a second, concurrent kernel
+    ws_bytes = int(_lib.lib().acfm_raster_fwd_workspace_bytes(N, H, W)) if SPLIT_FILL else 0
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     if _lib.event_hook is not None:
         _lib.event_hook("raster_fwd", 0)
     with torch.cuda.device(dev):
         st = _lib.lib().acfm_raster_fwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K,
                                         float(blur_radius), int(clip_barycentric_coords), int(cull_backfaces),
                                         float(sigma), _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), _lib.ptr(bary),
-                                        _lib.ptr(mask), _lib.stream_of(ndc))
+                                        _lib.ptr(mask), _lib.ptr(ws), ws_bytes, _lib.stream_of(ndc))
     _lib.check(st, "acfm_raster_fwd")
-    _lib.count()
+    _lib.count(3 if ws is not None else 1)
     if _lib.event_hook is not None:
         _lib.event_hook("raster_fwd", 1)
     return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask)

@@ -88,11 +88,18 @@ int acfm_softmax_cols_bwd(const float* y, const float* grad_y, int V, int K, flo
  *   bary (N,H,W,K,3) f32 or NULL;  mask (N,H,W) f32 or NULL (requires sigma > 0):
  *   mask = 1 - prod_k (1 - sigmoid(-dists_k / sigma)).
  * K <= 64.  Arithmetic is strict IEEE fp32 in PyTorch3D's CPU operator order.
+ *
+ * workspace: optional device scratch of acfm_raster_fwd_workspace_bytes(N,H,W) bytes (16-byte aligned, contents
+ *   irrelevant on entry, garbage on return).  With it the call classifies the (render, 32x32 region) units first and
+ *   writes the -1 padding of the units the mesh cannot touch from a second kernel that runs concurrently with the
+ *   rasterizer (forked from and joined back into `stream`; capturable in a CUDA graph).  NULL: one kernel does both.
+ *   Results are identical either way.
  * --------------------------------------------------------------------------------------------- */
 int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                     int N, int V, int F, int H, int W, int K, float blur_radius, int clip_bary,
                     int cull_backfaces, float sigma, int64_t* pix_to_face, float* zbuf, float* dists,
-                    float* bary, float* mask, void* stream);
+                    float* bary, float* mask, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W);
 
 /* Backward of rasterize_meshes + sigmoid_alpha_blend for the silhouette
  * (_C.rasterize_meshes_backward with grad only on dists).
