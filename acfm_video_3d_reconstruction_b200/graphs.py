@@ -40,3 +40,51 @@ class CapturedStep:
                 s.copy_(t, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class PrefetchedStep:
+    """Input pipeline around a CapturedStep: the pinned-host inputs of step i+1 are copied to the device on a copy stream
+    while step i replays, the way a training loop prefetches its next batch (DataLoader(pin_memory=True) + non_blocking
+    copies).  Two staging sets alternate; the replay takes its inputs from the staged set with device-to-device copies.
+
+        pipe = PrefetchedStep(captured)
+        pipe.prefetch(*host_inputs)                 # inputs of the first step
+        for batch in batches:
+            outs = pipe.run()                       # waits for the staged inputs only, then replays
+            pipe.prefetch(*next_host_inputs)        # H2D of the next step overlaps this step's kernels
+            ... read outs (D2H + synchronize) ...
+    """
+
+    def __init__(self, captured):
+        self.captured = captured
+        dev = captured.static_in[0].device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.staging = [[torch.empty_like(t) for t in captured.static_in] for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # H2D into staging[i] finished
+        self.consumed = [torch.cuda.Event() for _ in range(2)]   # staging[i] has been copied into the graph's inputs
+        self.head = 0      # set the next prefetch writes
+        self.pending = []  # staged sets not yet run, oldest first
+
+    def prefetch(self, *host_inputs):
+        if len(self.pending) == 2:
+            raise RuntimeError("PrefetchedStep: both staging sets are full; call run() first")
+        i = self.head
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[i])       # no-op for a never-recorded event
+            for s, t in zip(self.staging[i], host_inputs):
+                s.copy_(t, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self.pending.append(i)
+        self.head = 1 - i
+
+    def run(self):
+        if not self.pending:
+            raise RuntimeError("PrefetchedStep: run() without a prefetch()")
+        i = self.pending.pop(0)
+        cur = torch.cuda.current_stream(self.captured.static_in[0].device)
+        cur.wait_event(self.ready[i])
+        for s, t in zip(self.captured.static_in, self.staging[i]):
+            s.copy_(t, non_blocking=True)
+        self.consumed[i].record(cur)
+        self.captured.graph.replay()
+        return self.captured.static_out

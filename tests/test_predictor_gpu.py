@@ -124,3 +124,16 @@ def test_captured_training_step_equals_eager():
         assert util.rel_err(g.cpu().numpy(), w.cpu().numpy()) < 1e-4          # atomics order differs between runs
     got2 = cap(d0.cpu().pin_memory(), c0.cpu().pin_memory())   # pinned host inputs
     assert torch.allclose(got2[0], step(d0, c0)[0], rtol=1e-5)
+    # input pipeline: the staged inputs of three consecutive steps (pinned host) reach the right replay
+    pipe = graphs.PrefetchedStep(cap)
+    hosts = [(d.cpu().pin_memory(), c.cpu().pin_memory()) for d, c in ((d0, c0), (d1, c1), (d0 * 0.25, c0))]
+    pipe.prefetch(*hosts[0])
+    for i in range(3):
+        out = pipe.run()
+        if i + 1 < 3:
+            pipe.prefetch(*hosts[i + 1])          # overlaps the replay of step i
+        loss_i = float(out[0])                    # synchronises
+        want_i = float(step(hosts[i][0].to(dev), hosts[i][1].to(dev))[0])
+        assert abs(loss_i - want_i) <= 1e-5 * abs(want_i), (i, loss_i, want_i)
+    with pytest.raises(RuntimeError):
+        pipe.run()
