@@ -2,6 +2,7 @@
 usage: python scripts/summarize_profiles.py <tag>        (e.g. r01)
   gpurun_out/launches_<tag>.csv      -> profiles/launches_<tag>.csv (copy) + profiles/launches_<tag>.md (per-kernel shares)
   gpurun_out/prof_fwd_<tag>.ncu-rep  -> profiles/raster_fwd_<tag>.md  + traffic.json entry
+  gpurun_out/prof_fill_<tag>.ncu-rep -> profiles/raster_fill_<tag>.md + traffic.json entry
   gpurun_out/prof_bwd_<tag>.ncu-rep  -> profiles/raster_bwd_<tag>.md  + traffic.json entry
 """
 import collections
@@ -90,4 +91,14 @@ def full(kind, kname):
 
 launches()
 full("fwd", "raster_fwd_kernel")
+full("fill", "raster_fill_kernel")
 full("bwd", "raster_soft_bwd_kernel")
+# the forward op of the split path = raster_fwd_kernel (live regions) + raster_fill_kernel (padding of the empty regions), concurrent
+tj = os.path.join(PR, "traffic.json")
+if os.path.exists(tj):
+    d = json.load(open(tj))
+    c2 = d.get("C2", {})
+    if "raster_fwd_kernel" in c2 and "raster_fill_kernel" in c2:
+        c2["acfm_raster_fwd"] = c2["raster_fwd_kernel"] + c2["raster_fill_kernel"]
+        c2["acfm_raster_fwd_source"] = "sum of the raster_fwd_kernel and raster_fill_kernel captures (raster_prep_kernel: < 5 MB, not captured)"
+        json.dump(d, open(tj, "w"), indent=1)
