@@ -64,7 +64,7 @@ struct RasterParams {
   int regions_x, regions_y;
   int cap;      // face records per region
   int vec_ok;   // output pointers are 16-byte aligned
-  const int* work;  // split path: {countR, countF, -, -, listR[N*regions], listF[N*regions][2]} written by raster_prep_kernel
+  const int* work;  // split path: {countR, countF (runs), empty regions, -, listR[N*regions], listF[N*regions][2]} written by raster_prep_kernel
 };
 
 // shared-memory carve-up, identical on host and device
@@ -813,6 +813,7 @@ __global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterP
     if (lane == 0) {
       if (mr) br = atomicAdd(&ws[0], __popc(mr));
       if (mf) bf = atomicAdd(&ws[1], __popc(mf));
+      if (me) atomicAdd(&ws[2], __popc(me));  // empty regions (the runs' total length)
     }
     br = __shfl_sync(0xffffffffu, br, 0); bf = __shfl_sync(0xffffffffu, bf, 0);
     const unsigned lt = (1u << lane) - 1u;
@@ -859,7 +860,15 @@ __global__ void __launch_bounds__(kFillThreads) raster_fill_kernel(const RasterP
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
     __syncwarp();
   }
-  for (int w = blockIdx.x; w < countF; w += gridDim.x) {
+  // How many CTAs pad: the first half of the grid (one CTA on every other SM) writes ~3.3 TB/s, enough to finish under the
+  // rasterizer at the reference's workloads and gentler on it than one per SM (C2: 3.17 vs 3.32 ms); the second half joins
+  // only when the padding would otherwise outlast the rasterizer (sparse views: few live regions, many bytes to pad).
+  // Estimate: a live region costs the rasterizer ~0.37 us of the GPU (K = 20, reference templates), padding runs at 3.3 B/ps.
+  const long long pad_bytes = (long long)ws[2] * (kRegion * kRegion) * (16ll * K + 4);
+  const bool all_ctas = pad_bytes > (long long)ws[0] * 1200000ll;
+  const int nctas = all_ctas ? gridDim.x : max(1, (int)gridDim.x >> 1);
+  if ((int)blockIdx.x >= nctas) return;
+  for (int w = blockIdx.x; w < countF; w += nctas) {
     const int unit = listF[2 * w], run = listF[2 * w + 1];
     const int n = unit / regions, rg = unit - n * regions;
     const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
@@ -986,7 +995,7 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
     ACFM_CUDA_OK(cudaStreamWaitEvent(fj->side, fj->fork, 0));
     static const int fill_per_sm = getenv("ACFM_FILL_PER_SM") ? std::max(1, atoi(getenv("ACFM_FILL_PER_SM"))) : 1;
     static const int fill_abs = getenv("ACFM_FILL_CTAS") ? atoi(getenv("ACFM_FILL_CTAS")) : 0;
-    const int fill_ctas = fill_abs > 0 ? fill_abs : (int)std::min<long long>(ctas, (long long)fj->sms * fill_per_sm / 2);
+    const int fill_ctas = fill_abs > 0 ? fill_abs : (int)std::min<long long>(ctas, (long long)fj->sms * fill_per_sm);
     // bulk stores need 16-byte aligned rows: aligned bases, W*K (and so every row start) a multiple of 4 fragment slots
     const int bulk_ok = p.vec_ok && (((long long)W * K) & 3) == 0 && (!bary || (((uintptr_t)bary) & 15u) == 0) &&
                         getenv("ACFM_FILL_LSU") == nullptr;
