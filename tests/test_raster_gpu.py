@@ -253,3 +253,38 @@ def test_torch_dense_standin_matches_oracle():
     assert (p2f.cpu().numpy() != ref["pix_to_face"]).mean() < 1e-3
     (mask * torch.from_numpy(gm).cuda()).sum().backward()
     assert util.rel_err(nd.grad.cpu().numpy(), g_ref) < 1e-3
+
+
+@pytest.mark.parametrize("S,K,hard", [(256, 20, False), (100, 5, False), (90, 3, False), (256, 1, True), (72, 1, True), (512, 50, False)])
+def test_split_path_equals_single_kernel(S, K, hard, monkeypatch):
+    """acfm_raster_fwd with a workspace (region classification + rasterizer on the live regions + concurrent TMA padding
+    kernel, runs of empty regions) writes byte for byte what the single-kernel path writes: image sizes that are not
+    multiples of the region (and, at S = 90 / K = 3, rows that are not 16-byte multiples, which take the plain-store
+    fallback of the fill kernel), K = 1 with barycentrics, the largest K of the reference's configs; one render has no
+    vertex on screen (all regions empty), one fills the image (no empty region)."""
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("bird")
+    N = 6
+    X, cam = util.synth_verts(v, N, seed=5), util.synth_cams(N, seed=6)
+    cam[1, 1:3] = (3.0, -3.0)      # off screen
+    cam[2, 0] = 3.0                # larger than the image
+    cam[3, 1:3] = (0.8, 0.0)       # half outside
+    ndc = F_.project(torch.from_numpy(X).cuda(), torch.from_numpy(cam).cuda(), 5.0, -1.0, -1.0, F_.EYE_Z)
+    faces = torch.from_numpy(f)[None].cuda()
+
+    def render():
+        if hard:
+            return F_.rasterize(ndc, faces, S, 0.0, 1, clip_barycentric_coords=True, want_bary=True)
+        return F_.rasterize(ndc, faces, S, F_.BLUR_SOFT, K, sigma=F_.SIGMA, want_mask=True)
+
+    monkeypatch.setattr(F_, "SPLIT_FILL", True)
+    a = render()
+    monkeypatch.setattr(F_, "SPLIT_FILL", False)
+    b = render()
+    torch.cuda.synchronize()
+    for key in ("pix_to_face", "zbuf", "dists", "bary", "mask"):
+        if a[key] is None:
+            assert b[key] is None
+            continue
+        assert torch.equal(a[key], b[key]), key
+    assert (a["pix_to_face"][1] == -1).all() and (a["pix_to_face"][0] >= 0).any()
