@@ -26,7 +26,7 @@ SIGNATURES = {
     "acfm_softmax_cols_fwd": [_c_vp, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_softmax_cols_bwd": [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_raster_fwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int,
-                        _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
+                        _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "acfm_raster_fwd_workspace_bytes": [_c_int, _c_int, _c_int],
     "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],

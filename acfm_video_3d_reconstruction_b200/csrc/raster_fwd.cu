@@ -61,6 +61,7 @@ struct RasterParams {
   float* dists;
   float* bary;
   float* mask;
+  float* vis;   // optional (N,V): 1 for the vertices of every pixel's nearest face (zeroed by the host entry)
   int regions_x, regions_y;
   int cap;      // face records per region
   int vec_ok;   // output pointers are 16-byte aligned
@@ -621,6 +622,17 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
       if (p.mask && valid) p.mask[((long long)n * p.H + yi) * p.W + xi] = 0.0f;
       continue;
     }
+    if (p.vis && cnt > 0) {
+      // visible vertices = vertices of the faces that are nearest at some pixel (the fi_maps -> unique -> scatter_ block
+      // of bds_loss / optical_flow_loss, loss_utils.py:213-223,432-441): one lane per distinct face of the tile stores
+      const unsigned fv = (unsigned)lk[0];
+      const unsigned peers = __match_any_sync(__activemask(), fv);
+      if (__ffs(peers) - 1 == lane) {
+        const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
+        float* vo = p.vis + (size_t)n * p.V;
+        vo[(int)fp[0]] = 1.0f; vo[(int)fp[1]] = 1.0f; vo[(int)fp[2]] = 1.0f;
+      }
+    }
     if (p.mask && valid) {
       float alpha = 1.0f;
       for (int i = 0; i < cnt; ++i) {
@@ -950,7 +962,7 @@ extern "C" int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, in
 extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N,
                                int V, int F, int H, int W, int K, float blur_radius, int clip_bary, int cull_backfaces,
                                float sigma, int64_t* pix_to_face, float* zbuf, float* dists, float* bary, float* mask,
-                               void* workspace, int64_t workspace_bytes, void* stream) {
+                               float* visible_verts, void* workspace, int64_t workspace_bytes, void* stream) {
   ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: bad sizes N=%d V=%d F=%d H=%d W=%d", N, V, F, H, W);
   ACFM_REQUIRE(K >= 1, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: faces_per_pixel K=%d must be >= 1", K);
   ACFM_REQUIRE(K <= 64, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: faces_per_pixel K=%d > 64 is not supported", K);
@@ -966,7 +978,7 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   p.N = N; p.V = V; p.F = F; p.H = H; p.W = W; p.K = K;
   p.blur = blur_radius; p.sq_blur = sqrtf(blur_radius); p.sigma = sigma;
   p.clip = clip_bary; p.cull = cull_backfaces;
-  p.p2f = (long long*)pix_to_face; p.zbuf = zbuf; p.dists = dists; p.bary = bary; p.mask = mask;
+  p.p2f = (long long*)pix_to_face; p.zbuf = zbuf; p.dists = dists; p.bary = bary; p.mask = mask; p.vis = visible_verts;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
   p.vec_ok = ((((uintptr_t)pix_to_face) | ((uintptr_t)zbuf) | ((uintptr_t)dists)) & 15u) == 0;
   int smem = 0, cap = 0;
@@ -977,6 +989,7 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   const long long ctas = (long long)N * p.regions_x * p.regions_y;
   ACFM_REQUIRE(ctas < (1ll << 28), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: too many CTAs");
   cudaStream_t st = (cudaStream_t)stream;
+  if (visible_verts && V > 0) ACFM_CUDA_OK(cudaMemsetAsync(visible_verts, 0, sizeof(float) * (size_t)N * V, st));
   // split path (see raster_prep_kernel): needs the caller's scratch; without it everything runs in the one kernel
   static const bool no_split = getenv("ACFM_FWD_NOSPLIT") != nullptr;
   static const char* only = getenv("ACFM_FWD_ONLY");  // timing hook: "raster" / "fill" launches just that half (wrong outputs)

@@ -91,10 +91,12 @@ def project(verts, cams, offset_z=0.0, sx=1.0, sy=1.0, z_add=0.0):
 # kernel, see include/acfm_b200.h); False: the single-kernel path.  Same results; a switch for tests and A/B timing.
 SPLIT_FILL = os.environ.get("ACFM_SPLIT_FILL", "1") != "0"
 
+
 def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycentric_coords=False,
-              cull_backfaces=False, sigma=0.0, want_bary=False, want_mask=False):
+              cull_backfaces=False, sigma=0.0, want_bary=False, want_mask=False, want_vis=False):
     """rasterize_meshes on screen-space verts (no autograd).  Returns dict of pix_to_face / zbuf / dists
-    [/ bary / mask]."""
+    [/ bary / mask / vis].  vis (N,V): vertices of the faces nearest at some pixel, a by-product of the render that
+    loss_utils.bds_loss / optical_flow_loss otherwise recompute from pix_to_face[..., 0] (a strided 1 GB read at C3)."""
     _lib.require_cuda(ndc, faces)
     ndc = _f32c(ndc)
     N, V, _ = ndc.shape
@@ -107,6 +109,7 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
     dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
     bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if want_bary else None
     mask = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_mask else None
+    vis = torch.empty((N, V), dtype=torch.float32, device=dev) if want_vis else None
     # scratch of the split path (region work lists): the empty regions are padded by a second, concurrent kernel
     ws_bytes = int(_lib.lib().acfm_raster_fwd_workspace_bytes(N, H, W)) if SPLIT_FILL else 0
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
@@ -116,34 +119,39 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
         st = _lib.lib().acfm_raster_fwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K,
                                         float(blur_radius), int(clip_barycentric_coords), int(cull_backfaces),
                                         float(sigma), _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), _lib.ptr(bary),
-                                        _lib.ptr(mask), _lib.ptr(ws), ws_bytes, _lib.stream_of(ndc))
+                                        _lib.ptr(mask), _lib.ptr(vis), _lib.ptr(ws), ws_bytes, _lib.stream_of(ndc))
     _lib.check(st, "acfm_raster_fwd")
-    _lib.count(3 if ws is not None else 1)
+    _lib.count((3 if ws is not None else 1) + (1 if vis is not None else 0))
+    if vis is not None:
+        p2f._acfm_vis = vis   # picked up by loss_utils.visible_vertices
     if _lib.event_hook is not None:
         _lib.event_hook("raster_fwd", 1)
-    return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask)
+    return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask, vis=vis)
 
 
 class _SoftSilhouette(torch.autograd.Function):
     """ndc (N,V,3) -> mask (N,H,W), pix_to_face, zbuf, dists; differentiable in ndc through dists."""
 
     @staticmethod
-    def forward(ctx, ndc, faces, image_size, blur_radius, K, sigma):
-        fr = rasterize(ndc, faces, image_size, blur_radius, K, sigma=sigma, want_mask=True)
+    def forward(ctx, ndc, faces, image_size, blur_radius, K, sigma, want_vis=False):
+        fr = rasterize(ndc, faces, image_size, blur_radius, K, sigma=sigma, want_mask=True, want_vis=want_vis)
         ctx.save_for_backward(ndc.contiguous(), faces, fr["pix_to_face"], fr["dists"], fr["mask"])
         ctx.cfg = (int(image_size), int(K), float(sigma))
         ctx.mark_non_differentiable(fr["pix_to_face"], fr["zbuf"], fr["dists"])
         ctx.set_materialize_grads(False)
+        if want_vis:
+            ctx.mark_non_differentiable(fr["vis"])
+            return fr["mask"], fr["pix_to_face"], fr["zbuf"], fr["dists"], fr["vis"]
         return fr["mask"], fr["pix_to_face"], fr["zbuf"], fr["dists"]
 
     @staticmethod
-    def backward(ctx, grad_mask, _g1, _g2, _g3):
+    def backward(ctx, grad_mask, _g1, _g2, _g3, _g4=None):
         ndc, faces, p2f, dists, mask = ctx.saved_tensors
         S, K, sigma = ctx.cfg
         N, V, _ = ndc.shape
         fa, i64, fstride, F = _faces_arg(faces, N)
         if grad_mask is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         grad_mask = _f32c(grad_mask)
         g = torch.empty_like(ndc)
         if _lib.event_hook is not None:
@@ -156,8 +164,14 @@ class _SoftSilhouette(torch.autograd.Function):
         _lib.count(2)  # memset + kernel
         if _lib.event_hook is not None:
             _lib.event_hook("raster_bwd", 1)
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None
 
 
-def soft_silhouette(ndc, faces, image_size, blur_radius=BLUR_SOFT, faces_per_pixel=K_SOFT, sigma=SIGMA):
-    return _SoftSilhouette.apply(ndc, faces, int(image_size), float(blur_radius), int(faces_per_pixel), float(sigma))
+def soft_silhouette(ndc, faces, image_size, blur_radius=BLUR_SOFT, faces_per_pixel=K_SOFT, sigma=SIGMA, want_vis=False):
+    """-> mask, pix_to_face, zbuf, dists.  want_vis: the render also marks the visible vertices; the (N,V) map rides on the
+    returned pix_to_face tensor (attribute `_acfm_vis`), where loss_utils.bds_loss finds it."""
+    out = _SoftSilhouette.apply(ndc, faces, int(image_size), float(blur_radius), int(faces_per_pixel), float(sigma), bool(want_vis))
+    if want_vis:
+        out[1]._acfm_vis = out[4]
+        return out[:4]
+    return out

@@ -127,6 +127,9 @@ def visible_vertices(pix_to_face, faces, num_verts):
     """(N,V) 0/1 floats: vertices of the faces that are nearest at some pixel — the fi_maps/unique/scatter_ block of
     bds_loss (loss_utils.py:213-223) and optical_flow_loss (:432-441).  pix_to_face (N,H,W,K) int64 packed ids."""
     _lib.require_cuda(pix_to_face, faces)
+    fused = getattr(pix_to_face, "_acfm_vis", None)   # written by the render itself (functional.rasterize(want_vis=True))
+    if fused is not None and fused.shape == (pix_to_face.shape[0], num_verts):
+        return fused
     if pix_to_face.dtype != torch.int64:
         pix_to_face = pix_to_face.long()
     pix_to_face = pix_to_face.contiguous()
@@ -249,7 +252,7 @@ def optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=
     with torch.no_grad():
         if pix_to_face is None:
             pix_to_face = renderer(predicted_points.reshape(bt, nv, 3), faces_bt)
-        else:
+        elif getattr(pix_to_face, "_acfm_vis", None) is None:
             pix_to_face = pix_to_face[..., :1]
         vis = visible_vertices(pix_to_face, faces_bt, nv)
     flows_bt = flows.reshape(-1, flows.shape[2], flows.shape[3], flows.shape[4])

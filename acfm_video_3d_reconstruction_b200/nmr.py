@@ -29,6 +29,9 @@ class NeuralRenderer(torch.nn.Module):
         self.sigma = F_.SIGMA
         self.blur_radius = F_.BLUR_SOFT
         self.faces_per_pixel = F_.K_SOFT
+        # True: the mask render also marks the visible vertices (rides on the returned pix_to_face; bds_loss uses it
+        # instead of re-reading pix_to_face[..., 0]).  Set it where the boundary loss follows the render (multiframe).
+        self.emit_visibility = False
 
     def ambient_light_only(self):
         return
@@ -49,7 +52,7 @@ class NeuralRenderer(torch.nn.Module):
         if textures is None:
             self.mask_only = True
             masks, pix_to_face, _, _ = F_.soft_silhouette(ndc, faces, self.img_size, self.blur_radius,
-                                                          self.faces_per_pixel, self.sigma)
+                                                          self.faces_per_pixel, self.sigma, want_vis=self.emit_visibility)
             return masks, pix_to_face
         self.mask_only = False
         from . import texture
@@ -75,5 +78,5 @@ class OF_NeuralRenderer(torch.nn.Module):
             # R = diag(-1,1,1), T = (0,0,2.732): exact sign flip, one rounding on z
             # no host-side constants here (keeps the call CUDA-graph capturable)
             ndc = torch.stack([-verts[..., 0], verts[..., 1], verts[..., 2] + F_.EYE_Z], dim=-1)
-            fr = F_.rasterize(ndc, faces, self.img_size, 0.0, 1)
+            fr = F_.rasterize(ndc, faces, self.img_size, 0.0, 1, want_vis=True)   # its only consumer needs the visibility
         return fr["pix_to_face"]

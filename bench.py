@@ -197,7 +197,8 @@ class HotPath:
             from acfm_video_3d_reconstruction_b200 import camera
             cam_pred = camera.assemble_cameras(cams, self.mirror, self.transforms, 0.05)
         pred_v, ndc = deform.deform_and_project(self.mean_v, W, delta, cam_pred, offset_z=cfg["offset_z"])
-        mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
+        mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA,
+                                             want_vis=full)   # the boundary loss below takes the visibility from the render
         ls = loss_utils.mask_losses(mask, target, edt)
         per = ls["l1"] + W_EDT * ls["edt"]
         if full:

@@ -86,7 +86,10 @@ int acfm_softmax_cols_bwd(const float* y, const float* grad_y, int V, int K, flo
  * Outputs, (N,H,W,K) row-major, -1 padded, sorted by (z, face) ascending:
  *   pix_to_face int64 packed ids n*F+f;  zbuf f32;  dists f32 signed squared NDC distance;
  *   bary (N,H,W,K,3) f32 or NULL;  mask (N,H,W) f32 or NULL (requires sigma > 0):
- *   mask = 1 - prod_k (1 - sigmoid(-dists_k / sigma)).
+ *   mask = 1 - prod_k (1 - sigmoid(-dists_k / sigma));
+ *   visible_verts (N,V) f32 or NULL: 1.0 for every vertex of a face that is the nearest fragment of some pixel, else 0 —
+ *   the `fi_maps -> faces_ -> unique -> scatter_` block of bds_loss / optical_flow_loss (multiframe/nnutils/loss_utils.py:
+ *   213-223, 432-441) as a by-product of the render (same result as acfm_visible_verts on pix_to_face[..., 0]).
  * K <= 64.  Arithmetic is strict IEEE fp32 in PyTorch3D's CPU operator order.
  *
  * workspace: optional device scratch of acfm_raster_fwd_workspace_bytes(N,H,W) bytes (16-byte aligned, contents
@@ -98,7 +101,8 @@ int acfm_softmax_cols_bwd(const float* y, const float* grad_y, int V, int K, flo
 int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                     int N, int V, int F, int H, int W, int K, float blur_radius, int clip_bary,
                     int cull_backfaces, float sigma, int64_t* pix_to_face, float* zbuf, float* dists,
-                    float* bary, float* mask, void* workspace, int64_t workspace_bytes, void* stream);
+                    float* bary, float* mask, float* visible_verts, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W);
 
 /* Backward of rasterize_meshes + sigmoid_alpha_blend for the silhouette

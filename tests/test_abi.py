@@ -31,9 +31,9 @@ def test_bad_arguments_return_status_not_crash():
     from acfm_video_3d_reconstruction_b200 import _lib
     lib = _lib.lib()
     # K = 0 and K > 64 are rejected before any CUDA call
-    st = lib.acfm_raster_fwd(None, None, 1, 0, 1, 3, 1, 8, 8, 0, 0.0, 0, 0, 0.0, None, None, None, None, None, None, 0, None)
+    st = lib.acfm_raster_fwd(None, None, 1, 0, 1, 3, 1, 8, 8, 0, 0.0, 0, 0, 0.0, None, None, None, None, None, None, None, 0, None)
     assert st == 1 and b"faces_per_pixel" in lib.acfm_last_error_string()
-    st = lib.acfm_raster_fwd(None, None, 1, 0, 1, 3, 1, 8, 8, 65, 0.0, 0, 0, 0.0, None, None, None, None, None, None, 0, None)
+    st = lib.acfm_raster_fwd(None, None, 1, 0, 1, 3, 1, 8, 8, 65, 0.0, 0, 0, 0.0, None, None, None, None, None, None, None, 0, None)
     assert st == 2
     with pytest.raises(ValueError):
         _lib.check(st, "acfm_raster_fwd")

@@ -288,3 +288,29 @@ def test_split_path_equals_single_kernel(S, K, hard, monkeypatch):
             continue
         assert torch.equal(a[key], b[key]), key
     assert (a["pix_to_face"][1] == -1).all() and (a["pix_to_face"][0] >= 0).any()
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_fused_visible_vertices_equal_the_pix_to_face_route(split, monkeypatch):
+    """The (N,V) visible-vertex map written by the render (vertices of every pixel's nearest face) equals what
+    acfm_visible_verts derives from pix_to_face[..., 0] — the reference's fi_maps/unique/scatter_ block — for the soft
+    K = 20 render (NeuralRenderer.emit_visibility) and the hard K = 1 render (OF_NeuralRenderer), and the losses pick it up."""
+    from acfm_video_3d_reconstruction_b200 import NeuralRenderer, OF_NeuralRenderer, loss_utils
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    monkeypatch.setattr(F_, "SPLIT_FILL", split)
+    v, f = util.template("horse")
+    N = 5
+    X, cam = util.synth_verts(v, N, seed=11), util.synth_cams(N, seed=12)
+    cam[1, 1:3] = (3.0, 3.0)   # off screen: nothing visible
+    Xc, cc = torch.from_numpy(X).cuda(), torch.from_numpy(cam).cuda()
+    faces = torch.from_numpy(f)[None].cuda().expand(N, -1, -1)
+    r = NeuralRenderer(128, offset_z=5.0)
+    r.emit_visibility = True
+    _, p2f = r(Xc, faces, cc)
+    fused = p2f._acfm_vis
+    assert loss_utils.visible_vertices(p2f, faces, v.shape[0]) is fused
+    plain = loss_utils.visible_vertices(p2f.clone(), faces, v.shape[0])      # a clone carries no attribute
+    assert torch.equal(fused, plain) and fused[1].sum() == 0 and 0 < fused[0].sum() < v.shape[0]
+    proj = F_.project(Xc, cc, 5.0)
+    p1 = OF_NeuralRenderer(128)(proj, faces)
+    assert torch.equal(p1._acfm_vis, loss_utils.visible_vertices(p1.clone(), faces, v.shape[0]))
