@@ -46,6 +46,7 @@
 
 namespace {
 
+static_assert(kRegion / kTileW == 4 && (kRegion / kTileW) * (kRegion / kTileH) == 32, "a region is 4 x 8 tiles: one lane / one bit each");
 constexpr int kZBuckets = 64;  // depth buckets of the region face list (front-to-back evaluation order)
 constexpr int kQueue = 32;     // per-lane candidate queue depth (record ids, 1 byte each)
 
@@ -70,14 +71,15 @@ struct RasterParams {
 
 // shared-memory carve-up, identical on host and device
 struct FwdSmem {
-  int off_ndc, off_red, off_hist, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
-  int w_k, w_d, w_q, w_cnt;  // offsets inside one warp's slab
+  int off_ndc, off_red, off_hist, off_tw, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
+  int w_k, w_d, w_q, w_cnt, w_ord;  // offsets inside one warp's slab
   int KS;                         // per-lane list stride (odd)
   __host__ __device__ FwdSmem(int V, int F, int K, int nwarps, int cap) {
     int o = 32;  // mbarrier + counters
     off_ndc = o; o += 2 * kRegion * 4;  // pixel-centre NDC coordinates of the region's columns and rows
     off_red = o; o += nwarps * 32;
     off_hist = o; o += kZBuckets * 4;
+    off_tw = o; o += 32 * 4;  // faces per 8x4 tile of the region (tile order: heaviest first)
     off_rlist = o; o += ((F * 2 + 15) / 16) * 16;  // ushort per region face
     off_recA = o; o += cap * 64;                   // 4 float4 arrays (scan / filter data)
     off_recB = o; o += cap * 64;                   // 4 float4 arrays (exact evaluation data)
@@ -91,6 +93,7 @@ struct FwdSmem {
     w_d = w; w += KS * 32 * 4;
     w_q = w; w += kQueue * 32;
     w_cnt = w; w += 32;
+    w_ord = w; w += 32;
     warp_bytes = w;
     total = off_union + max(nwarps * warp_bytes, vb + F * 4);  // the slabs alias the staging/bucketing scratch
   }
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
   float* ndc_y = ndc_x + kRegion;
   float* red = reinterpret_cast<float*>(smem + L.off_red);
   int* hist = reinterpret_cast<int*>(smem + L.off_hist);
+  int* tw = reinterpret_cast<int*>(smem + L.off_tw);
   unsigned short* rlist = reinterpret_cast<unsigned short*>(smem + L.off_rlist);
   float4* recA = reinterpret_cast<float4*>(smem + L.off_recA);  // [4][cap]: bbox | g0 g1.x | g1.yz g2.xy | g2.z
   float4* recB = reinterpret_cast<float4*>(smem + L.off_recB);  // [4][cap]: x0 y0 x1 y1 | x2 y2 z0 z1 | z2 den yden flags | r01 r02 r12
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
       red[warp * 8 + 4] = zlo; red[warp * 8 + 5] = zhi;
     }
     if (tid < kZBuckets) hist[tid] = 0;
+    if (tid < 32) tw[tid] = 0;
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) {
@@ -402,6 +407,14 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
       cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);
       return;
     }
+  }
+
+  // exact pixel-centre coordinates of the region's columns / rows (one division each, here only); entries past the image
+  // edge repeat the last pixel.  Visible to everyone after the barriers of step 2.
+  if (tid < 2 * kRegion) {
+    const int i = tid & (kRegion - 1);
+    if (tid < kRegion) ndc_x[i] = pix_to_ndc(p.W - 1 - min(px0 + i, p.W - 1), p.W);
+    else ndc_y[i] = pix_to_ndc(p.H - 1 - min(py0 + i, p.H - 1), p.H);
   }
 
   // ---- 2. cull all faces against the region; bucket the survivors front to back ------------------------
@@ -461,29 +474,46 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
   }
   __syncthreads();
 
-  // ---- 3. per-region face records; exact pixel-centre coordinates of the region (one division each, here only) ----
-  if (tid < 2 * kRegion) {
-    const int i = tid & (kRegion - 1);
-    if (tid < kRegion) ndc_x[i] = pix_to_ndc(p.W - 1 - min(px0 + i, p.W - 1), p.W);
-    else ndc_y[i] = pix_to_ndc(p.H - 1 - min(py0 + i, p.H - 1), p.H);
-  }
+  // ---- 3. per-region face records; faces per tile ----------------------------------------------------------
+  // While a face's record is written, its blur-expanded bounding box is tested against the region's 4 x 8 tiles (same
+  // comparisons as the per-pixel test) and the hits are counted per tile: lane t of every warp accumulates tile t.
+  // The counts order the tiles heaviest first (longest-processing-time-first over the CTA's warps: the warps of a
+  // region finish closer together) and let tiles that no face touches go straight to the padding.
   const int nrec = min(nlist, cap);
-  for (int j = tid; j < nrec; j += NT) {
-    const int f = rlist[j];
-    const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
-    const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
-    FaceSetup s;
-    setup_face(s, f, sv[i0 * 3], sv[i0 * 3 + 1], sv[i0 * 3 + 2], sv[i1 * 3], sv[i1 * 3 + 1], sv[i1 * 3 + 2], sv[i2 * 3],
-               sv[i2 * 3 + 1], sv[i2 * 3 + 2], p.blur, p.sq_blur);
-    recA[j] = make_float4(s.bxmin, s.bxmax, s.bymin, s.bymax);
-    recA[cap + j] = make_float4(s.g[0], s.g[1], s.g[2], s.g[3]);
-    recA[2 * cap + j] = make_float4(s.g[4], s.g[5], s.g[6], s.g[7]);
-    recA[3 * cap + j] = make_float4(s.g[8], 0.f, 0.f, 0.f);
-    recB[j] = make_float4(s.b.x0, s.b.y0, s.b.x1, s.b.y1);
-    recB[cap + j] = make_float4(s.b.x2, s.b.y2, s.b.z0, s.b.z1);
-    recB[2 * cap + j] = make_float4(s.b.z2, s.b.den, s.b.yden, __int_as_float(s.b.flags));
-    recB[3 * cap + j] = make_float4(s.b.r01, s.b.r02, s.b.r12, 0.f);
+  int tw_acc = 0;
+  for (int j0 = 0; j0 < nrec; j0 += NT) {
+    const int j = j0 + tid;
+    unsigned tm = 0u;
+    if (j < nrec) {
+      const int f = rlist[j];
+      const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
+      const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
+      FaceSetup s;
+      setup_face(s, f, sv[i0 * 3], sv[i0 * 3 + 1], sv[i0 * 3 + 2], sv[i1 * 3], sv[i1 * 3 + 1], sv[i1 * 3 + 2], sv[i2 * 3],
+                 sv[i2 * 3 + 1], sv[i2 * 3 + 2], p.blur, p.sq_blur);
+      recA[j] = make_float4(s.bxmin, s.bxmax, s.bymin, s.bymax);
+      recA[cap + j] = make_float4(s.g[0], s.g[1], s.g[2], s.g[3]);
+      recA[2 * cap + j] = make_float4(s.g[4], s.g[5], s.g[6], s.g[7]);
+      recA[3 * cap + j] = make_float4(s.g[8], 0.f, 0.f, 0.f);
+      recB[j] = make_float4(s.b.x0, s.b.y0, s.b.x1, s.b.y1);
+      recB[cap + j] = make_float4(s.b.x2, s.b.y2, s.b.z0, s.b.z1);
+      recB[2 * cap + j] = make_float4(s.b.z2, s.b.den, s.b.yden, __int_as_float(s.b.flags));
+      recB[3 * cap + j] = make_float4(s.b.r01, s.b.r02, s.b.r12, 0.f);
+      unsigned colm = 0u;
+#pragma unroll
+      for (int c = 0; c < kRegion / kTileW; ++c)
+        if (!(ndc_x[c * kTileW + kTileW - 1] > s.bxmax) && !(ndc_x[c * kTileW] < s.bxmin)) colm |= 1u << c;
+#pragma unroll
+      for (int r = 0; r < kRegion / kTileH; ++r)
+        if (!(ndc_y[r * kTileH + kTileH - 1] > s.bymax) && !(ndc_y[r * kTileH] < s.bymin)) tm |= colm << (r * (kRegion / kTileW));
+    }
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const unsigned b = __ballot_sync(0xffffffffu, (tm >> t) & 1u);
+      if (lane == t) tw_acc += __popc(b);
+    }
   }
+  if (tw_acc) atomicAdd(&tw[lane], tw_acc);
   __syncthreads();  // the staging scratch (verts, tmp) is dead from here on: the warp slabs alias it
 
   // ---- 4. warps pull 8x4 tiles; no CTA-wide synchronisation from here on ----------------------------
@@ -498,15 +528,29 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
   const int tiles_x = (px1 - px0 + kTileW - 1) / kTileW, tiles_y = (py1 - py0 + kTileH - 1) / kTileH;
   const int ntiles = tiles_x * tiles_y;
   const float inv_sigma_neg = p.sigma > 0.0f ? 1.0f / p.sigma : 0.0f;
+  // tile order of this region, heaviest first (every warp derives the same table for itself: no further CTA barrier).
+  // Lane t stands for tile t of the 4 x 8 grid; tiles outside the image sort last and are never reached (t < ntiles).
+  unsigned char* ordv = wslab + L.w_ord;
+  const int my_w = tw[lane];
+  {
+    const bool in_img = (lane & 3) < tiles_x && (lane >> 2) < tiles_y;
+    const int key = in_img ? ((my_w + 1) << 5) | (31 - lane) : 0;  // ties: raster order
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) rank += __shfl_sync(0xffffffffu, key, o) > key;
+    ordv[rank] = (unsigned char)lane;  // keys of image tiles are distinct; the others collide past ntiles, harmlessly
+    __syncwarp();
+  }
+  const bool has_overflow = nlist > nrec;
 
   while (true) {
     int t = 0;
     if (lane == 0) t = atomicAdd(next_tile, 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= ntiles) break;
-    // tiles_x is 4 for every full region: shift instead of the ~35-instruction integer division
-    const int trow = (tiles_x == kRegion / kTileW) ? (t >> 2) : (t / tiles_x);
-    const int tx0 = px0 + (t - trow * tiles_x) * kTileW, ty0 = py0 + trow * kTileH;
+    const int tbit = ordv[t];
+    const int trow = tbit >> 2;
+    const int tx0 = px0 + (tbit & 3) * kTileW, ty0 = py0 + trow * kTileH;
     const int xi = tx0 + (lane & 7), yi = ty0 + (lane >> 3);
     const bool valid = xi < p.W && yi < p.H;
     const int lx0 = tx0 - px0, ly0 = ty0 - py0;  // tile origin inside the region
@@ -518,7 +562,8 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
     unsigned long long last = 0ull;
 
     // (a)-(c): fill the per-lane queues face by face; drain them when one is full or the faces run out (one drain site)
-    int c0 = 0, cbase = 0;
+    // a tile that no record's bounding box touches (and no overflow face could) skips the scan: straight to the padding
+    int c0 = (!has_overflow && __shfl_sync(0xffffffffu, my_w, tbit) == 0) ? nrec : 0, cbase = 0;
     unsigned m = 0u;
     bool more = true;
     do {
