@@ -61,6 +61,10 @@ SIGNATURES = {
     "acfm_edge_rigidity_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_edge_rigidity_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
     "acfm_raster_fwd_launch_info": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],
+    "acfm_correlation_out_shape": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pi, _pi, _pi],
+    "acfm_correlation_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_correlation_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp,
+                             _c_vp, _c_vp],
 }
 
 _lib = None

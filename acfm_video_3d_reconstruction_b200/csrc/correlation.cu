@@ -1,0 +1,255 @@
+// correlation.cu — FlowNet-style correlation cost volume.
+//
+// Replaces the reference's only native code, the `correlation_cuda` extension of its frozen optical-flow network
+// (/root/reference/multiframe/data/optical_flow/model/correlation_package/correlation_cuda_kernel.cu:46-147 forward,
+// :150-334 backward; host side correlation_cuda.cc:9-104; module correlation.py:54-74; instantiated by
+// MaskFlownet.py:116,416 as Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)).
+// The reference builds it for sm_50..sm_75 (+ compute_70 PTX) and runs three kernels per call: two NCHW -> padded NHWC
+// copies and a one-warp-per-output-pixel dot product.
+//
+//   out[n, (tj+dr)*D + (ti+dr), oy, ox] = 1/(k*k*C) * sum_{j,i in [-kr,kr]} sum_c  P1[n, c, y1+j, x1+i] * P2[n, c, y1+j+tj*s2, x1+i+ti*s2]
+//   P = input zero-padded by `pad`, (y1,x1) = (oy,ox)*s1 + md, dr = md/s2, D = 2 dr + 1, kr = (k-1)/2,
+//   outH = ceil((H + 2 pad - 2 (kr + md)) / s1)          (correlation_cuda.cc:24-32)
+//
+// Here: no padded copies (bounds are tested while the tiles are staged), and for the network's configuration
+// (k = 1, s1 = s2 = 1, D = 9) a register-tiled kernel: a CTA owns a 32 x 8 tile of output pixels, stages 8 channels of the
+// in1 tile and of the in2 halo tile (16 x 40) in shared memory at a time, and each thread accumulates 4 pixels x 3 rows of
+// displacements x 9 columns of displacements = 108 dot products in registers — 10 LDS.128 per 108 FMA, against one shared /
+// global load per FMA in the reference kernel.  Everything else goes through a plain one-thread-per-output kernel.
+// fp32 accumulation like the reference (`float acc0`), divided by k*k*C at the end.  The backward is the exact adjoint
+// (equal to the reference's for stride1 = 1; the reference only ever runs this op under no_grad, multiframe/main.py:386-411).
+#include "common.cuh"
+
+namespace {
+
+struct CorrParams {
+  const float* in1;
+  const float* in2;
+  float* out;
+  int B, C, H, W, pad, k, md, s1, s2, kr, dr, D, outH, outW;
+  float nelems;
+};
+
+// ---- generic forward: one thread per output element ---------------------------------------------------
+__global__ void __launch_bounds__(256) corr_fwd_generic_kernel(const CorrParams p) {
+  const long long total = (long long)p.B * p.D * p.D * p.outH * p.outW;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % p.outW);
+  const int oy = (int)((idx / p.outW) % p.outH);
+  const int tc = (int)((idx / ((long long)p.outW * p.outH)) % (p.D * p.D));
+  const int n = (int)(idx / ((long long)p.outW * p.outH * p.D * p.D));
+  const int tj = tc / p.D - p.dr, ti = tc % p.D - p.dr;
+  const int y1 = oy * p.s1 + p.md - p.pad, x1 = ox * p.s1 + p.md - p.pad;  // unpadded coordinates
+  const int y2 = y1 + tj * p.s2, x2 = x1 + ti * p.s2;
+  const size_t plane = (size_t)p.H * p.W;
+  const float* a = p.in1 + (size_t)n * p.C * plane;
+  const float* b = p.in2 + (size_t)n * p.C * plane;
+  float acc = 0.0f;
+  for (int j = -p.kr; j <= p.kr; ++j) {
+    for (int i = -p.kr; i <= p.kr; ++i) {
+      const int ya = y1 + j, xa = x1 + i, yb = y2 + j, xb = x2 + i;
+      if (ya < 0 || ya >= p.H || xa < 0 || xa >= p.W || yb < 0 || yb >= p.H || xb < 0 || xb >= p.W) continue;  // zero padding
+      const float* pa = a + (size_t)ya * p.W + xa;
+      const float* pb = b + (size_t)yb * p.W + xb;
+      for (int c = 0; c < p.C; ++c) acc = fmaf(pa[c * plane], pb[c * plane], acc);
+    }
+  }
+  p.out[idx] = acc / p.nelems;
+}
+
+// ---- the network's configuration: k = 1, s1 = s2 = 1, dr = 4 (81 displacements) ----------------------
+constexpr int kTX = 32, kTY = 8, kCC = 8, kDR = 4, kD = 9;
+constexpr int kHaloW = kTX + 2 * kDR, kHaloH = kTY + 2 * kDR;  // 40 x 16
+constexpr int kCorrThreads = (kTX / 4) * kTY * 3;              // 4 pixels x 3 displacement rows per thread: 192
+
+__global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const CorrParams p) {
+  __shared__ __align__(16) float s1[kCC][kTY][kTX];
+  __shared__ __align__(16) float s2[kCC][kHaloH][kHaloW];
+  const int tid = threadIdx.x;
+  const int gx = tid & 7, gy = (tid >> 3) & 7, tg = tid >> 6;  // pixel group (4 wide), row, displacement-row group
+  const int n = blockIdx.z;
+  const int ox0 = blockIdx.x * kTX, oy0 = blockIdx.y * kTY;
+  const int off = p.md - p.pad;  // output pixel (oy, ox) sits at unpadded (oy + off, ox + off)
+  const size_t plane = (size_t)p.H * p.W;
+  const float* a = p.in1 + (size_t)n * p.C * plane;
+  const float* b = p.in2 + (size_t)n * p.C * plane;
+
+  float acc[3][4][kD];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < kD; ++i) acc[t][q][i] = 0.0f;
+
+  for (int c0 = 0; c0 < p.C; c0 += kCC) {
+    // stage kCC channels: the in1 tile and the in2 halo tile, zero outside the image (the reference's zero padding)
+    for (int e = tid; e < kCC * kTY * kTX; e += kCorrThreads) {
+      const int x = e % kTX, y = (e / kTX) % kTY, c = e / (kTX * kTY);
+      const int yy = oy0 + y + off, xx = ox0 + x + off;
+      float v = 0.0f;
+      if (c0 + c < p.C && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = a[(size_t)(c0 + c) * plane + (size_t)yy * p.W + xx];
+      s1[c][y][x] = v;
+    }
+    for (int e = tid; e < kCC * kHaloH * kHaloW; e += kCorrThreads) {
+      const int x = e % kHaloW, y = (e / kHaloW) % kHaloH, c = e / (kHaloW * kHaloH);
+      const int yy = oy0 + y + off - kDR, xx = ox0 + x + off - kDR;
+      float v = 0.0f;
+      if (c0 + c < p.C && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = b[(size_t)(c0 + c) * plane + (size_t)yy * p.W + xx];
+      s2[c][y][x] = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int c = 0; c < kCC; ++c) {
+      const float4 av = *reinterpret_cast<const float4*>(&s1[c][gy][gx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const float* row = &s2[c][gy + tg * 3 + t][gx * 4];
+        const float4 v0 = *reinterpret_cast<const float4*>(row), v1 = *reinterpret_cast<const float4*>(row + 4),
+                     v2 = *reinterpret_cast<const float4*>(row + 8);
+        const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int i = 0; i < kD; ++i) acc[t][q][i] = fmaf(aa[q], v[q + i], acc[t][q][i]);
+      }
+    }
+    __syncthreads();
+  }
+
+  const int oy = oy0 + gy, ox = ox0 + gx * 4;
+  if (oy >= p.outH || ox >= p.outW) return;
+  const size_t oplane = (size_t)p.outH * p.outW;
+  float* o = p.out + (size_t)n * kD * kD * oplane + (size_t)oy * p.outW + ox;
+  const bool vec = (ox + 3 < p.outW) && ((p.outW & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+#pragma unroll
+    for (int i = 0; i < kD; ++i) {
+      float* d = o + (size_t)((tg * 3 + t) * kD + i) * oplane;
+      const float r0 = acc[t][0][i] / p.nelems, r1 = acc[t][1][i] / p.nelems, r2 = acc[t][2][i] / p.nelems, r3 = acc[t][3][i] / p.nelems;
+      if (vec) {
+        *reinterpret_cast<float4*>(d) = make_float4(r0, r1, r2, r3);
+      } else {
+        d[0] = r0;
+        if (ox + 1 < p.outW) d[1] = r1;
+        if (ox + 2 < p.outW) d[2] = r2;
+        if (ox + 3 < p.outW) d[3] = r3;
+      }
+    }
+  }
+}
+
+// ---- backward: exact adjoint, one thread per input element ---------------------------------------------
+// grad_in1[n,c,y,x] = 1/nelems * sum over (tc, j, i) with (oy,ox)*s1 + md + (j,i) = (y,x) + pad of
+//                     grad_out[n,tc,oy,ox] * P2[n,c, y + tj*s2, x + ti*s2]
+// grad_in2[n,c,y,x] = 1/nelems * sum over (tc, j, i) with (oy,ox)*s1 + md + (j,i) + (tj,ti)*s2 = (y,x) + pad of
+//                     grad_out[n,tc,oy,ox] * P1[n,c, y - tj*s2, x - ti*s2]
+template <bool SECOND>
+__global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrParams p, const float* __restrict__ gout, float* __restrict__ gin) {
+  const long long total = (long long)p.B * p.C * p.H * p.W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % p.W), y = (int)((idx / p.W) % p.H);
+  const int c = (int)((idx / ((long long)p.W * p.H)) % p.C);
+  const int n = (int)(idx / ((long long)p.W * p.H * p.C));
+  const size_t plane = (size_t)p.H * p.W, oplane = (size_t)p.outH * p.outW;
+  const float* other = (SECOND ? p.in1 : p.in2) + ((size_t)n * p.C + c) * plane;
+  const float* go = gout + (size_t)n * p.D * p.D * oplane;
+  float acc = 0.0f;
+  for (int tc = 0; tc < p.D * p.D; ++tc) {
+    const int dj = (tc / p.D - p.dr) * p.s2, di = (tc % p.D - p.dr) * p.s2;
+    // the partner sample of the other input
+    const int yo = SECOND ? y - dj : y + dj, xo = SECOND ? x - di : x + di;
+    if (yo < 0 || yo >= p.H || xo < 0 || xo >= p.W) continue;  // zero padding
+    const float w = other[(size_t)yo * p.W + xo];
+    // (y1, x1) + (j, i) in padded coordinates of input 1
+    const int Y = (SECOND ? y - dj : y) + p.pad, X = (SECOND ? x - di : x) + p.pad;
+    for (int j = -p.kr; j <= p.kr; ++j) {
+      const int ny = Y - j - p.md;
+      if (ny < 0 || ny % p.s1 != 0) continue;
+      const int oy = ny / p.s1;
+      if (oy >= p.outH) continue;
+      for (int i = -p.kr; i <= p.kr; ++i) {
+        const int nx = X - i - p.md;
+        if (nx < 0 || nx % p.s1 != 0) continue;
+        const int ox = nx / p.s1;
+        if (ox >= p.outW) continue;
+        acc = fmaf(go[(size_t)tc * oplane + (size_t)oy * p.outW + ox], w, acc);
+      }
+    }
+  }
+  gin[idx] = acc / p.nelems;
+}
+
+int corr_setup(CorrParams& p, const char* who, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2) {
+  ACFM_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, ACFM_ERR_BAD_ARG, "%s: bad sizes B=%d C=%d H=%d W=%d", who, B, C, H, W);
+  ACFM_REQUIRE(pad >= 0 && k >= 1 && (k & 1) == 1 && md >= 0 && s1 >= 1 && s2 >= 1, ACFM_ERR_BAD_ARG,
+               "%s: pad_size >= 0, odd kernel_size >= 1, max_displacement >= 0, strides >= 1 expected", who);
+  p.B = B; p.C = C; p.H = H; p.W = W; p.pad = pad; p.k = k; p.md = md; p.s1 = s1; p.s2 = s2;
+  p.kr = (k - 1) / 2; p.dr = md / s2; p.D = 2 * p.dr + 1;
+  const int span_h = H + 2 * pad - 2 * (p.kr + md), span_w = W + 2 * pad - 2 * (p.kr + md);
+  ACFM_REQUIRE(span_h > 0 && span_w > 0, ACFM_ERR_BAD_ARG, "%s: the padded input is smaller than the correlation border", who);
+  ACFM_REQUIRE(p.kr <= md, ACFM_ERR_UNSUPPORTED, "%s: kernel radius %d > max_displacement %d reads outside the padded input in the reference too", who, p.kr, md);
+  p.outH = (span_h + s1 - 1) / s1; p.outW = (span_w + s1 - 1) / s1;
+  p.nelems = (float)(k * k * C);
+  return ACFM_OK;
+}
+
+}  // namespace
+
+extern "C" int acfm_correlation_out_shape(int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                                          int* channels, int* out_h, int* out_w) {
+  CorrParams p;
+  const int rc = corr_setup(p, "acfm_correlation_out_shape", 1, 1, H, W, pad_size, kernel_size, max_displacement, stride1, stride2);
+  if (rc != ACFM_OK) return rc;
+  if (channels) *channels = p.D * p.D;
+  if (out_h) *out_h = p.outH;
+  if (out_w) *out_w = p.outW;
+  return ACFM_OK;
+}
+
+extern "C" int acfm_correlation_fwd(const float* input1, const float* input2, int B, int C, int H, int W, int pad_size, int kernel_size,
+                                    int max_displacement, int stride1, int stride2, float* output, void* stream) {
+  CorrParams p;
+  const int rc = corr_setup(p, "acfm_correlation_fwd", B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2);
+  if (rc != ACFM_OK) return rc;
+  if (B == 0) return ACFM_OK;
+  ACFM_REQUIRE(input1 && input2 && output, ACFM_ERR_BAD_ARG, "acfm_correlation_fwd: null pointer");
+  p.in1 = input1; p.in2 = input2; p.out = output;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool force_generic = getenv("ACFM_CORR_GENERIC") != nullptr;
+  if (kernel_size == 1 && stride1 == 1 && stride2 == 1 && p.dr == kDR && B <= 65535 && !force_generic) {
+    const dim3 grid((p.outW + kTX - 1) / kTX, (p.outH + kTY - 1) / kTY, B);
+    ACFM_REQUIRE(grid.y <= 65535, ACFM_ERR_UNSUPPORTED, "acfm_correlation_fwd: output too tall");
+    corr_fwd_d9_kernel<<<grid, kCorrThreads, 0, st>>>(p);
+    ACFM_LAUNCH_OK("corr_fwd_d9_kernel");
+  } else {
+    const long long total = (long long)B * p.D * p.D * p.outH * p.outW;
+    ACFM_REQUIRE((total + 255) / 256 < (1ll << 31), ACFM_ERR_UNSUPPORTED, "acfm_correlation_fwd: output too large");
+    corr_fwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+    ACFM_LAUNCH_OK("corr_fwd_generic_kernel");
+  }
+  return ACFM_OK;
+}
+
+extern "C" int acfm_correlation_bwd(const float* input1, const float* input2, const float* grad_output, int B, int C, int H, int W,
+                                    int pad_size, int kernel_size, int max_displacement, int stride1, int stride2, float* grad_input1,
+                                    float* grad_input2, void* stream) {
+  CorrParams p;
+  const int rc = corr_setup(p, "acfm_correlation_bwd", B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2);
+  if (rc != ACFM_OK) return rc;
+  if (B == 0) return ACFM_OK;
+  ACFM_REQUIRE(input1 && input2 && grad_output && (grad_input1 || grad_input2), ACFM_ERR_BAD_ARG, "acfm_correlation_bwd: null pointer");
+  p.in1 = input1; p.in2 = input2; p.out = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * C * H * W;
+  ACFM_REQUIRE((total + 255) / 256 < (1ll << 31), ACFM_ERR_UNSUPPORTED, "acfm_correlation_bwd: input too large");
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (grad_input1) corr_bwd_kernel<false><<<blocks, 256, 0, st>>>(p, grad_output, grad_input1);
+  if (grad_input2) corr_bwd_kernel<true><<<blocks, 256, 0, st>>>(p, grad_output, grad_input2);
+  ACFM_LAUNCH_OK("corr_bwd_kernel");
+  return ACFM_OK;
+}

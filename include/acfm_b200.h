@@ -274,6 +274,25 @@ int acfm_edge_rigidity_fwd(const float* verts, const float* tmpl, const void* ed
 int acfm_edge_rigidity_bwd(const float* verts, const float* tmpl, const void* edges, int edges_i64, const float* grad_loss, int N,
                            int NT, int V, int E, float* grad_verts, float* grad_tmpl, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Correlation cost volume.  Replaces the reference's `correlation_cuda` extension
+ * (multiframe/data/optical_flow/model/correlation_package/correlation_cuda.cc:9-104 forward, :106-170 backward;
+ * kernels correlation_cuda_kernel.cu:46-334; module correlation.py:54-74), used by its frozen flow network as
+ * Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1) (MaskFlownet.py:116,416).
+ *   input1, input2 (B,C,H,W) f32 contiguous;  output (B, D*D, outH, outW), D = 2*(max_displacement/stride2)+1,
+ *   outH = ceil((H + 2*pad_size - 2*((kernel_size-1)/2 + max_displacement)) / stride1)  (acfm_correlation_out_shape):
+ *   output[n,(tj+dr)*D+(ti+dr),oy,ox] = 1/(k*k*C) sum_{j,i,c} P1[n,c,y1+j,x1+i] * P2[n,c,y1+j+tj*stride2,x1+i+ti*stride2],
+ *   P = zero-padded input, (y1,x1) = (oy,ox)*stride1 + max_displacement.  corr_type_multiply is always 1 in the reference.
+ * Backward: exact adjoint (grad_input1 / grad_input2 may be NULL to skip one), overwritten.
+ * --------------------------------------------------------------------------------------------- */
+int acfm_correlation_out_shape(int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                               int* channels, int* out_h, int* out_w);
+int acfm_correlation_fwd(const float* input1, const float* input2, int B, int C, int H, int W, int pad_size, int kernel_size,
+                         int max_displacement, int stride1, int stride2, float* output, void* stream);
+int acfm_correlation_bwd(const float* input1, const float* input2, const float* grad_output, int B, int C, int H, int W,
+                         int pad_size, int kernel_size, int max_displacement, int stride1, int stride2, float* grad_input1,
+                         float* grad_input2, void* stream);
+
 /* Query: dynamic shared memory (bytes) and CTAs the forward rasterizer launches for a shape
  * (host-only helper used by bench.py for the launch/roofline accounting). */
 int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes,

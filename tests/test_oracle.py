@@ -234,3 +234,21 @@ def test_prior_losses_restatement_vs_reference_golden():
     Xd = X.double().requires_grad_(True)
     torch_ref.laplacian_smoothing_cot(Xd, hf).backward()
     assert util.rel_err(Xd.grad.numpy(), g["smooth_grad_X"]) < 1e-4   # the constant weights are fp32 on both sides (summation order differs)
+
+
+def test_correlation_restatement_closed_form():
+    """oracle/correlation_ref.py on cases with a known answer (CPU): output shape formula of correlation_cuda.cc:24-32, the
+    centre displacement of identical inputs is the per-pixel mean square, a shifted copy peaks at its shift, zero padding."""
+    import torch
+    from oracle import correlation_ref as cref
+    assert cref.out_shape(64, 64, 4, 1, 4, 1, 1) == (81, 64, 64)
+    assert cref.out_shape(24, 24, 20, 1, 20, 2, 2) == (441, 12, 12)
+    assert cref.out_shape(18, 22, 3, 3, 2, 1, 1) == (25, 18, 22)
+    x = torch.randn(2, 5, 10, 12, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    c = cref.correlation(x, x, 4, 1, 4, 1, 1)
+    assert c.shape == (2, 81, 10, 12)
+    assert torch.allclose(c[:, 40], (x * x).mean(1))
+    assert torch.allclose(c[:, 0, :4, :], torch.zeros(2, 4, 12, dtype=torch.float64))        # displacement (-4,-4): rows 0..3 read padding
+    y = torch.roll(x, shifts=(1, 2), dims=(2, 3))
+    c = cref.correlation(x, y, 4, 1, 4, 1, 1)[:, :, 4:6, 4:8].mean(dim=(0, 2, 3))
+    assert int(c.argmax()) == (1 + 4) * 9 + (2 + 4)
