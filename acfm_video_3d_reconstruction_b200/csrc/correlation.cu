@@ -27,7 +27,7 @@ struct CorrParams {
   const float* in2;
   float* out;
   int B, C, H, W, pad, k, md, s1, s2, kr, dr, D, outH, outW;
-  float nelems;
+  float nelems, inv_nelems;
 };
 
 // ---- generic forward: one thread per output element ---------------------------------------------------
@@ -58,11 +58,21 @@ __global__ void __launch_bounds__(256) corr_fwd_generic_kernel(const CorrParams 
   p.out[idx] = acc / p.nelems;
 }
 
+// 4-byte asynchronous global -> shared copy; !valid: the destination is zero-filled and the source is not read
+__device__ __forceinline__ void cp_async_f32(float* dst_smem, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_f32x4(float* dst_smem, const float* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+
 // ---- the network's configuration: k = 1, s1 = s2 = 1, dr = 4 (81 displacements) ----------------------
 constexpr int kTX = 32, kTY = 8, kCC = 8, kDR = 4, kD = 9;
 constexpr int kHaloW = kTX + 2 * kDR, kHaloH = kTY + 2 * kDR;  // 40 x 16
 constexpr int kCorrThreads = (kTX / 4) * kTY * 3;              // 4 pixels x 3 displacement rows per thread: 192
 
+template <bool VEC>
 __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const CorrParams p) {
   __shared__ __align__(16) float s1[kCC][kTY][kTX];
   __shared__ __align__(16) float s2[kCC][kHaloH][kHaloW];
@@ -84,21 +94,50 @@ __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const Corr
       for (int i = 0; i < kD; ++i) acc[t][q][i] = 0.0f;
 
   for (int c0 = 0; c0 < p.C; c0 += kCC) {
-    // stage kCC channels: the in1 tile and the in2 halo tile, zero outside the image (the reference's zero padding)
-    for (int e = tid; e < kCC * kTY * kTX; e += kCorrThreads) {
-      const int x = e % kTX, y = (e / kTX) % kTY, c = e / (kTX * kTY);
-      const int yy = oy0 + y + off, xx = ox0 + x + off;
-      float v = 0.0f;
-      if (c0 + c < p.C && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = a[(size_t)(c0 + c) * plane + (size_t)yy * p.W + xx];
-      s1[c][y][x] = v;
+    // stage kCC channels: the in1 tile and the in2 halo tile, zero outside the image (the reference's zero padding).
+    // The copies are asynchronous (cp.async, zero-filling form for the padding), so all of a chunk's loads are in flight
+    // at once and no register is needed to carry them past the 108 accumulators.  Unaligned shapes: 4-byte copies, one
+    // warp per (channel, row).
+    if (VEC) {
+      // rows start 16-byte aligned (W, the tile origin and md - pad are multiples of 4): 16-byte copies, each wholly inside
+      // or wholly outside the image
+      for (int e = tid; e < kCC * kTY * (kTX / 4); e += kCorrThreads) {
+        const int xv = e % (kTX / 4), y = (e / (kTX / 4)) % kTY, c = e / ((kTX / 4) * kTY);
+        const int yy = oy0 + y + off, xx = ox0 + xv * 4 + off;
+        const bool ok = (c0 + c < p.C) && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        cp_async_f32x4(&s1[c][y][xv * 4], a + (ok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W + xx : 0), ok);
+      }
+      for (int e = tid; e < kCC * kHaloH * (kHaloW / 4); e += kCorrThreads) {
+        const int xv = e % (kHaloW / 4), y = (e / (kHaloW / 4)) % kHaloH, c = e / ((kHaloW / 4) * kHaloH);
+        const int yy = oy0 + y + off - kDR, xx = ox0 + xv * 4 + off - kDR;
+        const bool ok = (c0 + c < p.C) && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        cp_async_f32x4(&s2[c][y][xv * 4], b + (ok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W + xx : 0), ok);
+      }
+    } else {
+      const int lane = tid & 31, wrp = tid >> 5;
+      constexpr int kWarps = kCorrThreads / 32;
+      for (int r = wrp; r < kCC * kTY; r += kWarps) {
+        const int c = r / kTY, y = r - c * kTY;
+        const int yy = oy0 + y + off, xx = ox0 + lane + off;
+        const bool rowok = (c0 + c < p.C) && yy >= 0 && yy < p.H;
+        const float* src = a + (rowok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W : 0);
+        const bool ok = rowok && xx >= 0 && xx < p.W;
+        cp_async_f32(&s1[c][y][lane], src + (ok ? xx : 0), ok);
+      }
+      for (int r = wrp; r < kCC * kHaloH; r += kWarps) {
+        const int c = r / kHaloH, y = r - c * kHaloH;
+        const int yy = oy0 + y + off - kDR, xx = ox0 + lane + off - kDR;
+        const bool rowok = (c0 + c < p.C) && yy >= 0 && yy < p.H;
+        const float* src = b + (rowok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W : 0);
+        const bool ok0 = rowok && xx >= 0 && xx < p.W;
+        cp_async_f32(&s2[c][y][lane], src + (ok0 ? xx : 0), ok0);
+        if (lane < kHaloW - 32) {
+          const bool ok1 = rowok && xx + 32 >= 0 && xx + 32 < p.W;
+          cp_async_f32(&s2[c][y][32 + lane], src + (ok1 ? xx + 32 : 0), ok1);
+        }
+      }
     }
-    for (int e = tid; e < kCC * kHaloH * kHaloW; e += kCorrThreads) {
-      const int x = e % kHaloW, y = (e / kHaloW) % kHaloH, c = e / (kHaloW * kHaloH);
-      const int yy = oy0 + y + off - kDR, xx = ox0 + x + off - kDR;
-      float v = 0.0f;
-      if (c0 + c < p.C && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = b[(size_t)(c0 + c) * plane + (size_t)yy * p.W + xx];
-      s2[c][y][x] = v;
-    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 #pragma unroll 2
     for (int c = 0; c < kCC; ++c) {
@@ -129,7 +168,7 @@ __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const Corr
 #pragma unroll
     for (int i = 0; i < kD; ++i) {
       float* d = o + (size_t)((tg * 3 + t) * kD + i) * oplane;
-      const float r0 = acc[t][0][i] / p.nelems, r1 = acc[t][1][i] / p.nelems, r2 = acc[t][2][i] / p.nelems, r3 = acc[t][3][i] / p.nelems;
+      const float r0 = acc[t][0][i] * p.inv_nelems, r1 = acc[t][1][i] * p.inv_nelems, r2 = acc[t][2][i] * p.inv_nelems, r3 = acc[t][3][i] * p.inv_nelems;
       if (vec) {
         *reinterpret_cast<float4*>(d) = make_float4(r0, r1, r2, r3);
       } else {
@@ -195,6 +234,7 @@ int corr_setup(CorrParams& p, const char* who, int B, int C, int H, int W, int p
   ACFM_REQUIRE(p.kr <= md, ACFM_ERR_UNSUPPORTED, "%s: kernel radius %d > max_displacement %d reads outside the padded input in the reference too", who, p.kr, md);
   p.outH = (span_h + s1 - 1) / s1; p.outW = (span_w + s1 - 1) / s1;
   p.nelems = (float)(k * k * C);
+  p.inv_nelems = (float)(1.0 / (double)(k * k * C));  // the tiled kernel multiplies (exact for power-of-two C, else within 1 ulp of the division)
   return ACFM_OK;
 }
 
@@ -224,7 +264,9 @@ extern "C" int acfm_correlation_fwd(const float* input1, const float* input2, in
   if (kernel_size == 1 && stride1 == 1 && stride2 == 1 && p.dr == kDR && B <= 65535 && !force_generic) {
     const dim3 grid((p.outW + kTX - 1) / kTX, (p.outH + kTY - 1) / kTY, B);
     ACFM_REQUIRE(grid.y <= 65535, ACFM_ERR_UNSUPPORTED, "acfm_correlation_fwd: output too tall");
-    corr_fwd_d9_kernel<<<grid, kCorrThreads, 0, st>>>(p);
+    const bool vec = (W & 3) == 0 && ((p.md - p.pad) & 3) == 0 && ((((uintptr_t)input1) | ((uintptr_t)input2)) & 15u) == 0;
+    if (vec) corr_fwd_d9_kernel<true><<<grid, kCorrThreads, 0, st>>>(p);
+    else corr_fwd_d9_kernel<false><<<grid, kCorrThreads, 0, st>>>(p);
     ACFM_LAUNCH_OK("corr_fwd_d9_kernel");
   } else {
     const long long total = (long long)B * p.D * p.D * p.outH * p.outW;

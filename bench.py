@@ -400,6 +400,7 @@ def run_ours(args):
     if world == 1:
         out["target_maps"] = target_maps_bench(hp, cfg, peak, cpu=not args.no_cpu_baseline)
         out["post_optimize"] = post_optimize_bench(hp, cfg, cpu=not args.no_cpu_baseline)
+        out["correlation"] = correlation_bench(hp, peak)
         if not args.no_cpu_baseline:
             out["gpu_standin"] = gpu_standin_bench(hp, cfg)
     if world == 1 and not args.no_cpu_baseline:
@@ -443,6 +444,66 @@ def target_maps_bench(hp, cfg, peak, cpu=True, iters=10):
         dt = time.time() - t
         out["cpu_baseline"] = {"value": len(mn) / dt, "unit": "masks/s", "cores": 1, "kind": "port",
                                "sample": f"{len(mn)} masks, scipy.ndimage EDT x3 + restated find_boundaries, serial as in set_input"}
+    return out
+
+
+def correlation_bench(hp, peak, pairs=60, iters=20):
+    """Side measurement: the five correlation cost volumes of one MaskFlowNet forward (pyramid levels 6..2 of
+    a 256 x 256 frame pair: C = 196/128/96/64/32 at 4^2 .. 64^2, md = 4: MaskFlownet.py:97-116,266-355) for one GPU's share of a
+    C3 step (4 clips x 15 adjacent-frame pairs), ours against the reference's OWN extension compiled for sm_100a
+    (oracle/_ref/correlation_cuda.so), both timed with CUDA events on the same inputs."""
+    from acfm_video_3d_reconstruction_b200.correlation import Correlation
+    from oracle import correlation_ref as cref
+    levels = [(196, 4), (128, 8), (96, 16), (64, 32), (32, 64)]
+    gen = torch.Generator().manual_seed(0)
+    data = [(torch.randn(pairs, C, S, S, generator=gen).to(hp.device), torch.randn(pairs, C, S, S, generator=gen).to(hp.device)) for C, S in levels]
+    corr = Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
+    ref = cref.load_reference_extension()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    with torch.no_grad():
+        ours = timed(lambda: [corr(a, b) for a, b in data])
+        # the same five launches replayed from a CUDA graph: device time without the ~5 x 30 us of Python / ctypes per call
+        try:
+            side = torch.cuda.Stream(device=hp.device)
+            side.wait_stream(torch.cuda.current_stream(hp.device))
+            with torch.cuda.stream(side):
+                [corr(a, b) for a, b in data]
+            torch.cuda.current_stream(hp.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                keep = [corr(a, b) for a, b in data]
+            ours_graph = timed(g.replay)
+            del keep
+        except Exception:
+            ours_graph = None
+        per_level = [timed(lambda a=a, b=b: corr(a, b)) for a, b in data]
+        top = per_level[-1]
+        C, S = levels[-1]
+        alg = pairs * (2 * C + 81) * S * S * 4
+        out = {"unit": "ms per flow forward (5 cost volumes)", "pairs": pairs, "ms": ours, "ms_cuda_graph": ours_graph,
+               "pairs_per_s": pairs / ((ours_graph or ours) * 1e-3),
+               "ms_per_level_eager": {f"C{c}_{s}x{s}": t for (c, s), t in zip(levels, per_level)},
+               "largest_level": {"shape": [pairs, C, S, S], "ms": top, "alg_bytes": alg, "achieved_gbs": alg / (top * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": alg / (top * 1e-3) / 1e9 / peak,
+                                 "tflops": 2.0 * pairs * 81 * C * S * S / (top * 1e-3) / 1e12}}
+        if ref is not None:
+            r = timed(lambda: [cref.reference_forward(ref, a, b, 4, 1, 4, 1, 1) for a, b in data])
+            rl = [timed(lambda a=a, b=b: cref.reference_forward(ref, a, b, 4, 1, 4, 1, 1)) for a, b in data]
+            out["reference_extension"] = {"ms": r, "ms_per_level_eager": {f"C{c}_{s}x{s}": t for (c, s), t in zip(levels, rl)},
+                                          "kind": "reference (its own correlation_cuda_kernel.cu, compiled for sm_100a into oracle/_ref), eager",
+                                          "ours_speedup_eager": r / ours}
     return out
 
 
