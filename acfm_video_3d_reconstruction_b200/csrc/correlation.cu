@@ -13,7 +13,7 @@
 //
 // Here: no padded copies (bounds are tested while the tiles are staged), and for the network's configuration
 // (k = 1, s1 = s2 = 1, D = 9) a register-tiled kernel: a CTA owns a 32 x 8 tile of output pixels, stages 8 channels of the
-// in1 tile and of the in2 halo tile (16 x 40) in shared memory at a time, and each thread accumulates 4 pixels x 3 rows of
+// in1 tile and of the in2 halo tile (16 x 40) in shared memory at a time (3-stage cp.async pipeline), and each thread accumulates 4 pixels x 3 rows of
 // displacements x 9 columns of displacements = 108 dot products in registers — 10 LDS.128 per 108 FMA, against one shared /
 // global load per FMA in the reference kernel.  Everything else goes through a plain one-thread-per-output kernel.
 // fp32 accumulation like the reference (`float acc0`), divided by k*k*C at the end.  The backward is the exact adjoint
@@ -72,10 +72,13 @@ constexpr int kTX = 32, kTY = 8, kCC = 8, kDR = 4, kD = 9;
 constexpr int kHaloW = kTX + 2 * kDR, kHaloH = kTY + 2 * kDR;  // 40 x 16
 constexpr int kCorrThreads = (kTX / 4) * kTY * 3;              // 4 pixels x 3 displacement rows per thread: 192
 
+constexpr int kStages = 3;                                       // cp.async pipeline depth
+constexpr int kS1Floats = kCC * kTY * kTX, kS2Floats = kCC * kHaloH * kHaloW;
+constexpr int kCorrSmemBytes = kStages * (kS1Floats + kS2Floats) * 4;  // 84 KB: dynamic shared memory, 2 CTAs per SM
+
 template <bool VEC>
 __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const CorrParams p) {
-  __shared__ __align__(16) float s1[kCC][kTY][kTX];
-  __shared__ __align__(16) float s2[kCC][kHaloH][kHaloW];
+  extern __shared__ __align__(16) float corr_smem[];
   const int tid = threadIdx.x;
   const int gx = tid & 7, gy = (tid >> 3) & 7, tg = tid >> 6;  // pixel group (4 wide), row, displacement-row group
   const int n = blockIdx.z;
@@ -93,11 +96,13 @@ __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const Corr
 #pragma unroll
       for (int i = 0; i < kD; ++i) acc[t][q][i] = 0.0f;
 
-  for (int c0 = 0; c0 < p.C; c0 += kCC) {
-    // stage kCC channels: the in1 tile and the in2 halo tile, zero outside the image (the reference's zero padding).
-    // The copies are asynchronous (cp.async, zero-filling form for the padding), so all of a chunk's loads are in flight
-    // at once and no register is needed to carry them past the 108 accumulators.  Unaligned shapes: 4-byte copies, one
-    // warp per (channel, row).
+  // stage kCC channels starting at c0 into buffer `st`: the in1 tile and the in2 halo tile, zero outside the image (the
+  // reference's zero padding).  The copies are asynchronous (cp.async, zero-filling form for the padding): all of a chunk's
+  // loads are in flight at once, no register carries them past the 108 accumulators, and the next chunk's loads overlap this
+  // chunk's arithmetic.  Unaligned shapes: 4-byte copies, one warp per (channel, row).
+  auto stage = [&](int c0, int st) {
+    float* s1 = corr_smem + st * (kS1Floats + kS2Floats);   // [kCC][kTY][kTX]
+    float* s2 = s1 + kS1Floats;                              // [kCC][kHaloH][kHaloW]
     if (VEC) {
       // rows start 16-byte aligned (W, the tile origin and md - pad are multiples of 4): 16-byte copies, each wholly inside
       // or wholly outside the image
@@ -105,13 +110,13 @@ __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const Corr
         const int xv = e % (kTX / 4), y = (e / (kTX / 4)) % kTY, c = e / ((kTX / 4) * kTY);
         const int yy = oy0 + y + off, xx = ox0 + xv * 4 + off;
         const bool ok = (c0 + c < p.C) && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-        cp_async_f32x4(&s1[c][y][xv * 4], a + (ok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W + xx : 0), ok);
+        cp_async_f32x4(s1 + (c * kTY + y) * kTX + xv * 4, a + (ok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W + xx : 0), ok);
       }
       for (int e = tid; e < kCC * kHaloH * (kHaloW / 4); e += kCorrThreads) {
         const int xv = e % (kHaloW / 4), y = (e / (kHaloW / 4)) % kHaloH, c = e / ((kHaloW / 4) * kHaloH);
         const int yy = oy0 + y + off - kDR, xx = ox0 + xv * 4 + off - kDR;
         const bool ok = (c0 + c < p.C) && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-        cp_async_f32x4(&s2[c][y][xv * 4], b + (ok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W + xx : 0), ok);
+        cp_async_f32x4(s2 + (c * kHaloH + y) * kHaloW + xv * 4, b + (ok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W + xx : 0), ok);
       }
     } else {
       const int lane = tid & 31, wrp = tid >> 5;
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const Corr
         const bool rowok = (c0 + c < p.C) && yy >= 0 && yy < p.H;
         const float* src = a + (rowok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W : 0);
         const bool ok = rowok && xx >= 0 && xx < p.W;
-        cp_async_f32(&s1[c][y][lane], src + (ok ? xx : 0), ok);
+        cp_async_f32(s1 + (c * kTY + y) * kTX + lane, src + (ok ? xx : 0), ok);
       }
       for (int r = wrp; r < kCC * kHaloH; r += kWarps) {
         const int c = r / kHaloH, y = r - c * kHaloH;
@@ -130,22 +135,40 @@ __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const Corr
         const bool rowok = (c0 + c < p.C) && yy >= 0 && yy < p.H;
         const float* src = b + (rowok ? (size_t)(c0 + c) * plane + (size_t)yy * p.W : 0);
         const bool ok0 = rowok && xx >= 0 && xx < p.W;
-        cp_async_f32(&s2[c][y][lane], src + (ok0 ? xx : 0), ok0);
+        cp_async_f32(s2 + (c * kHaloH + y) * kHaloW + lane, src + (ok0 ? xx : 0), ok0);
         if (lane < kHaloW - 32) {
           const bool ok1 = rowok && xx + 32 >= 0 && xx + 32 < p.W;
-          cp_async_f32(&s2[c][y][32 + lane], src + (ok1 ? xx + 32 : 0), ok1);
+          cp_async_f32(s2 + (c * kHaloH + y) * kHaloW + 32 + lane, src + (ok1 ? xx + 32 : 0), ok1);
         }
       }
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // kStages - 1 chunks in flight ahead of the arithmetic; one commit group per iteration (empty past the last chunk), so
+  // "all but the newest kStages - 1 groups have landed" always means "this iteration's chunk has landed"
+#pragma unroll
+  for (int s0 = 0; s0 < kStages - 1; ++s0) {
+    if (s0 * kCC < p.C) stage(s0 * kCC, s0);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int buf = 0, nbuf = kStages - 1;
+  for (int c0 = 0; c0 < p.C; c0 += kCC) {
+    if (c0 + (kStages - 1) * kCC < p.C) stage(c0 + (kStages - 1) * kCC, nbuf);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
     __syncthreads();
+    const float* s1 = corr_smem + buf * (kS1Floats + kS2Floats);
+    const float* s2 = s1 + kS1Floats;
+    // threads whose four pixels lie outside the output (small pyramid levels fill a fraction of the tile) only help staging
+    const int nch = (oy0 + gy < p.outH && ox0 + gx * 4 < p.outW) ? kCC : 0;
 #pragma unroll 2
-    for (int c = 0; c < kCC; ++c) {
-      const float4 av = *reinterpret_cast<const float4*>(&s1[c][gy][gx * 4]);
+    for (int c = 0; c < nch; ++c) {
+      const float4 av = *reinterpret_cast<const float4*>(s1 + (c * kTY + gy) * kTX + gx * 4);
       const float aa[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
-        const float* row = &s2[c][gy + tg * 3 + t][gx * 4];
+        const float* row = s2 + (c * kHaloH + gy + tg * 3 + t) * kHaloW + gx * 4;
         const float4 v0 = *reinterpret_cast<const float4*>(row), v1 = *reinterpret_cast<const float4*>(row + 4),
                      v2 = *reinterpret_cast<const float4*>(row + 8);
         const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
@@ -155,7 +178,9 @@ __global__ void __launch_bounds__(kCorrThreads, 2) corr_fwd_d9_kernel(const Corr
           for (int i = 0; i < kD; ++i) acc[t][q][i] = fmaf(aa[q], v[q + i], acc[t][q][i]);
       }
     }
-    __syncthreads();
+    __syncthreads();  // everyone is done with `buf` before a later iteration's copies overwrite it
+    buf = (buf + 1 == kStages) ? 0 : buf + 1;
+    nbuf = (nbuf + 1 == kStages) ? 0 : nbuf + 1;
   }
 
   const int oy = oy0 + gy, ox = ox0 + gx * 4;
@@ -265,8 +290,14 @@ extern "C" int acfm_correlation_fwd(const float* input1, const float* input2, in
     const dim3 grid((p.outW + kTX - 1) / kTX, (p.outH + kTY - 1) / kTY, B);
     ACFM_REQUIRE(grid.y <= 65535, ACFM_ERR_UNSUPPORTED, "acfm_correlation_fwd: output too tall");
     const bool vec = (W & 3) == 0 && ((p.md - p.pad) & 3) == 0 && ((((uintptr_t)input1) | ((uintptr_t)input2)) & 15u) == 0;
-    if (vec) corr_fwd_d9_kernel<true><<<grid, kCorrThreads, 0, st>>>(p);
-    else corr_fwd_d9_kernel<false><<<grid, kCorrThreads, 0, st>>>(p);
+    static std::atomic<int> smem_v[kAcfmMaxDevices], smem_s[kAcfmMaxDevices];
+    if (vec) {
+      ACFM_CUDA_OK(acfm_ensure_smem(corr_fwd_d9_kernel<true>, kCorrSmemBytes, smem_v));
+      corr_fwd_d9_kernel<true><<<grid, kCorrThreads, kCorrSmemBytes, st>>>(p);
+    } else {
+      ACFM_CUDA_OK(acfm_ensure_smem(corr_fwd_d9_kernel<false>, kCorrSmemBytes, smem_s));
+      corr_fwd_d9_kernel<false><<<grid, kCorrThreads, kCorrSmemBytes, st>>>(p);
+    }
     ACFM_LAUNCH_OK("corr_fwd_d9_kernel");
   } else {
     const long long total = (long long)B * p.D * p.D * p.outH * p.outW;
