@@ -47,6 +47,7 @@
 namespace {
 
 static_assert(kRegion / kTileW == 4 && (kRegion / kTileW) * (kRegion / kTileH) == 32, "a region is 4 x 8 tiles: one lane / one bit each");
+constexpr int kWeightClasses = 4;  // split path: live regions by face count (raster_prep_kernel)
 constexpr int kZBuckets = 64;  // depth buckets of the region face list (front-to-back evaluation order)
 constexpr int kQueue = 32;     // per-lane candidate queue depth (record ids, 1 byte each)
 
@@ -66,7 +67,8 @@ struct RasterParams {
   int regions_x, regions_y;
   int cap;      // face records per region
   int vec_ok;   // output pointers are 16-byte aligned
-  const int* work;  // split path: {countR, countF (runs), empty regions, -, listR[N*regions], listF[N*regions][2]} written by raster_prep_kernel
+  const int* work;  // split path, written by raster_prep_kernel: {live, fill runs, empty regions, -, live per weight class [4],
+                    //   listR[4][N*regions], listF[N*regions][2]}
 };
 
 // shared-memory carve-up, identical on host and device
@@ -348,9 +350,19 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int regions = p.regions_x * p.regions_y;
   int unit = blockIdx.x;
-  if (p.work) {  // split path: only regions the mesh can touch reach this kernel (the others go to raster_fill_kernel)
-    if (unit >= p.work[0]) return;
-    unit = p.work[4 + unit];
+  if (p.work) {
+    // split path: only regions the mesh can touch reach this kernel (the others go to raster_fill_kernel), in four weight
+    // classes, heaviest first (raster_prep_kernel): the grid's last CTAs are light ones, which shortens the kernel's tail
+    const int U = p.N * regions;
+    int cls = 0;
+#pragma unroll
+    for (; cls < kWeightClasses; ++cls) {
+      const int c = p.work[4 + cls];
+      if (unit < c) break;
+      unit -= c;
+    }
+    if (cls == kWeightClasses) return;
+    unit = p.work[8 + cls * U + unit];
   }
   const int n = unit / regions;
   const int rg = unit - n * regions;
@@ -815,7 +827,9 @@ int launch_fwd(const RasterParams& p, int smem, int ctas, cudaStream_t st) {
 // stream overlaps the arithmetic (C2: 3.97 -> 3.17 ms; the rasterizer alone 3.08 ms, the fill alone 1.33 ms).
 constexpr int kPrepThreads = 128;
 
-__global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterParams p, int* ws) {
+template <typename IdxT>
+__global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterParams p, int* ws, int weigh) {
+  extern __shared__ int rcnt[];  // faces per region (weigh != 0)
   __shared__ float red[kPrepThreads / 32][4];
   __shared__ float box[4];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -843,8 +857,32 @@ __global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterP
   __syncthreads();
   const float bxmin = box[0], bxmax = box[1], bymin = box[2], bymax = box[3];
   const int regions = p.regions_x * p.regions_y;
-  int* listR = ws + 4;
-  int* listF = ws + 4 + p.N * regions;
+  const int U = p.N * regions;
+  int* listR = ws + 8;
+  int* listF = ws + 8 + kWeightClasses * U;
+  // Faces per region (blur-expanded bounding boxes; approximate pixel arithmetic — the counts only ORDER the rasterizer's
+  // work, heaviest regions first, they never decide what is rendered)
+  if (weigh) {
+    for (int r = tid; r < regions; r += kPrepThreads) rcnt[r] = 0;
+    __syncthreads();
+    const IdxT* fn = reinterpret_cast<const IdxT*>(p.faces) + (long long)n * p.faces_stride;
+    const float hw = 0.5f * (float)p.W, hh = 0.5f * (float)p.H;
+    for (int f = tid; f < p.F; f += kPrepThreads) {
+      const int i0 = (int)fn[f * 3], i1 = (int)fn[f * 3 + 1], i2 = (int)fn[f * 3 + 2];
+      const float x0 = v[i0 * 3], y0 = v[i0 * 3 + 1], x1 = v[i1 * 3], y1 = v[i1 * 3 + 1], x2 = v[i2 * 3], y2 = v[i2 * 3 + 1];
+      const float fx0 = fminf(fminf(x0, x1), x2) - p.sq_blur, fx1 = fmaxf(fmaxf(x0, x1), x2) + p.sq_blur;
+      const float fy0 = fminf(fminf(y0, y1), y2) - p.sq_blur, fy1 = fmaxf(fmaxf(y0, y1), y2) + p.sq_blur;
+      if (!(fx0 <= 1.0f && fx1 >= -1.0f && fy0 <= 1.0f && fy1 >= -1.0f)) continue;  // off screen (or NaN)
+      // pixel xi samples NDC x = 1 - (2 xi + 1) / W  =>  xi = (1 - x) W / 2 - 1/2
+      const int ca = max(0, (int)floorf((1.0f - fminf(fx1, 1.0f)) * hw - 0.5f)) / kRegion;
+      const int cb = min(p.W - 1, (int)ceilf((1.0f - fmaxf(fx0, -1.0f)) * hw - 0.5f)) / kRegion;
+      const int ra = max(0, (int)floorf((1.0f - fminf(fy1, 1.0f)) * hh - 0.5f)) / kRegion;
+      const int rb = min(p.H - 1, (int)ceilf((1.0f - fmaxf(fy0, -1.0f)) * hh - 0.5f)) / kRegion;
+      for (int r = ra; r <= rb; ++r)
+        for (int c = ca; c <= cb; ++c) atomicAdd(&rcnt[r * p.regions_x + c], 1);
+    }
+    __syncthreads();
+  }
   for (int r0 = 0; r0 < regions; r0 += kPrepThreads) {
     const int rg = r0 + tid;
     bool live = false, inr = rg < regions;
@@ -866,15 +904,25 @@ __global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterP
       run = min(stop ? __ffs(stop) - 1 : 32, p.regions_x - col);
     }
     const unsigned mf = __ballot_sync(0xffffffffu, start);
-    int br = 0, bf = 0;
+    int bf = 0;
     if (lane == 0) {
-      if (mr) br = atomicAdd(&ws[0], __popc(mr));
+      if (mr) atomicAdd(&ws[0], __popc(mr));
       if (mf) bf = atomicAdd(&ws[1], __popc(mf));
       if (me) atomicAdd(&ws[2], __popc(me));  // empty regions (the runs' total length)
     }
-    br = __shfl_sync(0xffffffffu, br, 0); bf = __shfl_sync(0xffffffffu, bf, 0);
+    bf = __shfl_sync(0xffffffffu, bf, 0);
     const unsigned lt = (1u << lane) - 1u;
-    if (inr && live) listR[br + __popc(mr & lt)] = n * regions + rg;
+    // live regions by weight class (a 32 x 32 region of the reference templates sees 130-175 faces on average, up to ~500)
+    const int wgt = (weigh && inr && live) ? rcnt[rg] : 0;
+    const int cls = wgt >= 280 ? 0 : (wgt >= 200 ? 1 : (wgt >= 130 ? 2 : 3));
+#pragma unroll
+    for (int k = 0; k < kWeightClasses; ++k) {
+      const unsigned mk = __ballot_sync(0xffffffffu, inr && live && cls == k);
+      int bk = 0;
+      if (lane == 0 && mk) bk = atomicAdd(&ws[4 + k], __popc(mk));
+      bk = __shfl_sync(0xffffffffu, bk, 0);
+      if (inr && live && cls == k) listR[k * U + bk + __popc(mk & lt)] = n * regions + rg;
+    }
     if (start) {
       const int e = bf + __popc(mf & lt);
       listF[2 * e] = n * regions + rg;
@@ -907,7 +955,7 @@ __global__ void __launch_bounds__(kFillThreads) raster_fill_kernel(const RasterP
   extern __shared__ __align__(128) unsigned char pat[];
   const int regions = p.regions_x * p.regions_y;
   const int countF = ws[1];
-  const int* listF = ws + 4 + p.N * regions;
+  const int* listF = ws + 8 + kWeightClasses * p.N * regions;
   const int lane = threadIdx.x;
   const int K = p.K, chunk = fill_pattern_slots(K);
   long long* pat8 = reinterpret_cast<long long*>(pat);                         // [chunk] int64 -1
@@ -1040,13 +1088,16 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   static const char* only = getenv("ACFM_FWD_ONLY");  // timing hook: "raster" / "fill" launches just that half (wrong outputs)
   ForkJoin* fj = nullptr;
   if (workspace && !no_split) {
-    ACFM_REQUIRE(workspace_bytes >= 16 + 12 * ctas && (((uintptr_t)workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
+    ACFM_REQUIRE(workspace_bytes >= 32 + 24 * ctas && (((uintptr_t)workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
                  "acfm_raster_fwd: workspace must be 16-byte aligned and hold acfm_raster_fwd_workspace_bytes() = %lld bytes",
-                 16 + 12 * ctas);
+                 32 + 24 * ctas);
     if (fork_join(&fj) != ACFM_OK) return ACFM_ERR_CUDA;
     int* ws = (int*)workspace;
-    ACFM_CUDA_OK(cudaMemsetAsync(ws, 0, 16, st));
-    raster_prep_kernel<<<N, kPrepThreads, 0, st>>>(p, ws);
+    ACFM_CUDA_OK(cudaMemsetAsync(ws, 0, 32, st));
+    const int nreg = p.regions_x * p.regions_y;
+    const int weigh = nreg * 4 <= 40 * 1024 && F > 0;  // the per-region counters must fit the default shared-memory window
+    if (faces_i64) raster_prep_kernel<long long><<<N, kPrepThreads, weigh ? nreg * 4 : 0, st>>>(p, ws, weigh);
+    else raster_prep_kernel<int><<<N, kPrepThreads, weigh ? nreg * 4 : 0, st>>>(p, ws, weigh);
     ACFM_LAUNCH_OK("raster_prep_kernel");
     p.work = ws;
     ACFM_CUDA_OK(cudaEventRecord(fj->fork, st));
@@ -1081,5 +1132,5 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
 
 extern "C" int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W) {
   if (N <= 0 || H <= 0 || W <= 0) return 0;
-  return 16 + 12 * (int64_t)N * ((W + kRegion - 1) / kRegion) * ((H + kRegion - 1) / kRegion);
+  return 32 + 24 * (int64_t)N * ((W + kRegion - 1) / kRegion) * ((H + kRegion - 1) / kRegion);
 }
