@@ -965,13 +965,13 @@ __global__ void __launch_bounds__(kFillThreads) raster_fill_kernel(const RasterP
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
     __syncwarp();
   }
-  // How many CTAs pad: the first half of the grid (one CTA on every other SM) writes ~3.3 TB/s, enough to finish under the
-  // rasterizer at the reference's workloads and gentler on it than one per SM (C2: 3.17 vs 3.32 ms); the second half joins
-  // only when the padding would otherwise outlast the rasterizer (sparse views: few live regions, many bytes to pad).
-  // Estimate: a live region costs the rasterizer ~0.37 us of the GPU (K = 20, reference templates), padding runs at 3.3 B/ps.
+  // How many CTAs pad: five eighths of the grid (one CTA on most SMs) write ~4 TB/s, enough to finish under the rasterizer at
+  // the reference's workloads and gentler on it than one per SM (C2, 74 / 92 / 110 / 148 CTAs: 2.95 / 2.79 / 2.80 / 2.85 ms);
+  // the rest joins only when the padding would otherwise outlast the rasterizer (sparse views: few live regions, many bytes
+  // to pad).  Estimate: a live region costs the rasterizer ~0.33 us of the GPU (K = 20, reference templates).
   const long long pad_bytes = (long long)ws[2] * (kRegion * kRegion) * (16ll * K + 4);
   const bool all_ctas = pad_bytes > (long long)ws[0] * 1200000ll;
-  const int nctas = all_ctas ? gridDim.x : max(1, (int)gridDim.x >> 1);
+  const int nctas = all_ctas ? gridDim.x : max(1, ((int)gridDim.x * 5) >> 3);
   if ((int)blockIdx.x >= nctas) return;
   for (int w = blockIdx.x; w < countF; w += nctas) {
     const int unit = listF[2 * w], run = listF[2 * w + 1];
