@@ -35,6 +35,7 @@ struct BwdParams {
   const float* grad_dists;  // FROM_MASK == false: upstream gradient per fragment (N,H,W,K)
   float* grad_ndc;
   int regions_x, regions_y;
+  const int* work;  // optional: the forward's work lists (live regions by weight class); NULL = every region
 };
 
 struct BwdSmem {
@@ -122,8 +123,23 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   unsigned short* alist = reinterpret_cast<unsigned short*>(smem + L.off_list);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int regions = p.regions_x * p.regions_y;
-  const int n = blockIdx.x / regions;
-  const int rg = blockIdx.x - n * regions;
+  int unit = blockIdx.x;
+  if (p.work) {
+    // the regions the forward found live (the others hold no fragment: nothing to differentiate), heaviest first — same
+    // lists, same layout as raster_fwd_kernel reads (raster_fwd.cu: {.., live per weight class [4] at [4], lists at [8]})
+    const int U = p.N * regions;
+    int cls = 0;
+#pragma unroll
+    for (; cls < kWeightClasses; ++cls) {
+      const int c = p.work[4 + cls];
+      if (unit < c) break;
+      unit -= c;
+    }
+    if (cls == kWeightClasses) return;
+    unit = p.work[8 + cls * U + unit];
+  }
+  const int n = unit / regions;
+  const int rg = unit - n * regions;
   const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
   const int K = p.K;
 
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
 namespace {
 int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                int N, int V, int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
-               const float* mask, const float* grad_mask, const float* grad_dists, float* grad_ndc, void* stream) {
+               const float* mask, const float* grad_mask, const float* grad_dists, float* grad_ndc, const void* work, void* stream) {
   ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0 && K >= 1, ACFM_ERR_BAD_ARG, "%s: bad sizes", who);
   ACFM_REQUIRE(!from_mask || sigma > 0.0f, ACFM_ERR_BAD_ARG, "%s: sigma must be > 0", who);
   ACFM_REQUIRE(faces_batch_stride == 0 || faces_batch_stride == (int64_t)F * 3, ACFM_ERR_BAD_ARG, "%s: faces_batch_stride must be 0 or F*3", who);
@@ -283,6 +299,7 @@ int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* fa
   p.N = N; p.V = V; p.F = F; p.H = H; p.W = W; p.K = K; p.sigma = from_mask ? sigma : 1.0f;
   p.p2f = (const long long*)pix_to_face; p.dists = dists; p.mask = mask; p.grad_mask = grad_mask; p.grad_dists = grad_dists;
   p.grad_ndc = grad_ndc;
+  p.work = (const int*)work;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
   const BwdSmem L(V, F);
   ACFM_REQUIRE(L.total <= 227 * 1024, ACFM_ERR_UNSUPPORTED, "%s: needs %d B of shared memory (max 232448)", who, L.total);
@@ -305,14 +322,14 @@ int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* fa
 extern "C" int acfm_raster_soft_bwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                                     int N, int V, int F, int H, int W, int K, float sigma, const int64_t* pix_to_face,
                                     const float* dists, const float* mask, const float* grad_mask, float* grad_ndc,
-                                    void* stream) {
+                                    const void* fwd_workspace, void* stream) {
   return launch_bwd("acfm_raster_soft_bwd", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma,
-                    pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, stream);
+                    pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, fwd_workspace, stream);
 }
 
 extern "C" int acfm_raster_dists_bwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                                      int N, int V, int F, int H, int W, int K, const int64_t* pix_to_face,
                                      const float* dists, const float* grad_dists, float* grad_ndc, void* stream) {
   return launch_bwd("acfm_raster_dists_bwd", false, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, 0.0f,
-                    pix_to_face, dists, nullptr, nullptr, grad_dists, grad_ndc, stream);
+                    pix_to_face, dists, nullptr, nullptr, grad_dists, grad_ndc, nullptr, stream);
 }

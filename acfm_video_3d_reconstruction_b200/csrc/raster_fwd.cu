@@ -47,7 +47,6 @@
 namespace {
 
 static_assert(kRegion / kTileW == 4 && (kRegion / kTileW) * (kRegion / kTileH) == 32, "a region is 4 x 8 tiles: one lane / one bit each");
-constexpr int kWeightClasses = 4;  // split path: live regions by face count (raster_prep_kernel)
 constexpr int kZBuckets = 64;  // depth buckets of the region face list (front-to-back evaluation order)
 constexpr int kQueue = 32;     // per-lane candidate queue depth (record ids, 1 byte each)
 
@@ -878,6 +877,7 @@ __global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterP
       const int cb = min(p.W - 1, (int)ceilf((1.0f - fmaxf(fx0, -1.0f)) * hw - 0.5f)) / kRegion;
       const int ra = max(0, (int)floorf((1.0f - fminf(fy1, 1.0f)) * hh - 0.5f)) / kRegion;
       const int rb = min(p.H - 1, (int)ceilf((1.0f - fmaxf(fy0, -1.0f)) * hh - 0.5f)) / kRegion;
+      if ((rb - ra + 1) * (cb - ca + 1) > 64) continue;  // a face this large weighs on every region alike; keeps the pass bounded
       for (int r = ra; r <= rb; ++r)
         for (int c = ca; c <= cb; ++c) atomicAdd(&rcnt[r * p.regions_x + c], 1);
     }
@@ -1084,10 +1084,9 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   cudaStream_t st = (cudaStream_t)stream;
   if (visible_verts && V > 0) ACFM_CUDA_OK(cudaMemsetAsync(visible_verts, 0, sizeof(float) * (size_t)N * V, st));
   // split path (see raster_prep_kernel): needs the caller's scratch; without it everything runs in the one kernel
-  static const bool no_split = getenv("ACFM_FWD_NOSPLIT") != nullptr;
   static const char* only = getenv("ACFM_FWD_ONLY");  // timing hook: "raster" / "fill" launches just that half (wrong outputs)
   ForkJoin* fj = nullptr;
-  if (workspace && !no_split) {
+  if (workspace) {
     ACFM_REQUIRE(workspace_bytes >= 32 + 24 * ctas && (((uintptr_t)workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
                  "acfm_raster_fwd: workspace must be 16-byte aligned and hold acfm_raster_fwd_workspace_bytes() = %lld bytes",
                  32 + 24 * ctas);

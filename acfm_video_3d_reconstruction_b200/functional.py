@@ -126,7 +126,7 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
         p2f._acfm_vis = vis   # picked up by loss_utils.visible_vertices
     if _lib.event_hook is not None:
         _lib.event_hook("raster_fwd", 1)
-    return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask, vis=vis)
+    return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask, vis=vis, work=ws)
 
 
 class _SoftSilhouette(torch.autograd.Function):
@@ -137,6 +137,7 @@ class _SoftSilhouette(torch.autograd.Function):
         fr = rasterize(ndc, faces, image_size, blur_radius, K, sigma=sigma, want_mask=True, want_vis=want_vis)
         ctx.save_for_backward(ndc.contiguous(), faces, fr["pix_to_face"], fr["dists"], fr["mask"])
         ctx.cfg = (int(image_size), int(K), float(sigma))
+        ctx.work = fr["work"]   # the forward's region work lists: the backward visits the live regions only, heaviest first
         ctx.mark_non_differentiable(fr["pix_to_face"], fr["zbuf"], fr["dists"])
         ctx.set_materialize_grads(False)
         if want_vis:
@@ -159,7 +160,7 @@ class _SoftSilhouette(torch.autograd.Function):
         with torch.cuda.device(ndc.device):
             st = _lib.lib().acfm_raster_soft_bwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma,
                                                  _lib.ptr(p2f), _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(grad_mask),
-                                                 _lib.ptr(g), _lib.stream_of(ndc))
+                                                 _lib.ptr(g), _lib.ptr(ctx.work), _lib.stream_of(ndc))
         _lib.check(st, "acfm_raster_soft_bwd")
         _lib.count(2)  # memset + kernel
         if _lib.event_hook is not None:

@@ -93,7 +93,7 @@ int acfm_softmax_cols_bwd(const float* y, const float* grad_y, int V, int K, flo
  * K <= 64.  Arithmetic is strict IEEE fp32 in PyTorch3D's CPU operator order.
  *
  * workspace: optional device scratch of acfm_raster_fwd_workspace_bytes(N,H,W) bytes (16-byte aligned, contents
- *   irrelevant on entry, garbage on return).  With it the call classifies the (render, 32x32 region) units first and
+ *   irrelevant on entry; on return it holds the call's region work lists, which acfm_raster_soft_bwd can reuse).  With it the call classifies the (render, 32x32 region) units first and
  *   writes the -1 padding of the units the mesh cannot touch from a second kernel that runs concurrently with the
  *   rasterizer (forked from and joined back into `stream`; capturable in a CUDA graph).  NULL: one kernel does both.
  *   Results are identical either way.
@@ -107,11 +107,14 @@ int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W);
 
 /* Backward of rasterize_meshes + sigmoid_alpha_blend for the silhouette
  * (_C.rasterize_meshes_backward with grad only on dists).
- * grad_mask (N,H,W); grad_ndc (N,V,3) is overwritten (z component = 0). */
+ * grad_mask (N,H,W); grad_ndc (N,V,3) is overwritten (z component = 0).
+ * fwd_workspace: NULL, or the workspace acfm_raster_fwd was given for THIS render, untouched since (it then holds the lists of
+ * regions that contain fragments, heaviest first): the backward launches work for those only.  Same result either way. */
 int acfm_raster_soft_bwd(const float* ndc, const void* faces, int faces_i64,
                          int64_t faces_batch_stride, int N, int V, int F, int H, int W, int K,
                          float sigma, const int64_t* pix_to_face, const float* dists,
-                         const float* mask, const float* grad_mask, float* grad_ndc, void* stream);
+                         const float* mask, const float* grad_mask, float* grad_ndc,
+                         const void* fwd_workspace, void* stream);
 
 /* Backward of rasterize_meshes for an upstream gradient on dists only (grad_dists (N,H,W,K)); used by the
  * texture branch.  Gradients on zbuf / bary are not propagated: the reference's callers render textures

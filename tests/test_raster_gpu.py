@@ -314,3 +314,25 @@ def test_fused_visible_vertices_equal_the_pix_to_face_route(split, monkeypatch):
     proj = F_.project(Xc, cc, 5.0)
     p1 = OF_NeuralRenderer(128)(proj, faces)
     assert torch.equal(p1._acfm_vis, loss_utils.visible_vertices(p1.clone(), faces, v.shape[0]))
+
+
+def test_backward_with_forward_work_lists_equals_full_grid(monkeypatch):
+    """acfm_raster_soft_bwd visiting only the regions the forward found live (its work lists, heaviest first) gives the
+    gradient of the full-grid launch: the skipped regions hold no fragment.  One render is off screen, one fills the image."""
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("bird")
+    N, S = 6, 160
+    X, cam = util.synth_verts(v, N, seed=21), util.synth_cams(N, seed=22)
+    cam[1, 1:3] = (3.0, -3.0)
+    cam[2, 0] = 3.0
+    ndc = F_.project(torch.from_numpy(X).cuda(), torch.from_numpy(cam).cuda(), 5.0, -1.0, -1.0, F_.EYE_Z).detach()
+    faces = torch.from_numpy(f)[None].cuda()
+    g = torch.randn(N, S, S, generator=torch.Generator().manual_seed(1)).cuda()
+    grads = []
+    for split in (True, False):
+        monkeypatch.setattr(F_, "SPLIT_FILL", split)
+        x = ndc.clone().requires_grad_(True)
+        mask, _, _, _ = F_.soft_silhouette(x, faces, S)
+        grads.append(torch.autograd.grad((mask * g).sum(), x)[0])
+    assert grads[0][1].abs().sum() == 0 and grads[0][0].abs().sum() > 0
+    assert util.rel_err(grads[0].cpu().numpy(), grads[1].cpu().numpy()) < 1e-5
