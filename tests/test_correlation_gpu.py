@@ -123,3 +123,35 @@ def test_errors_and_edge_cases():
     y = torch.roll(x, shifts=(2, -3), dims=(2, 3))                       # y[p + (2,-3)] = x[p]
     cost = Correlation(4, 1, 4, 1, 1)(x, y)[0, :, 8:16, 8:16].mean(dim=(1, 2))
     assert int(cost.argmax()) == (2 + 4) * 9 + (-3 + 4)
+
+
+@pytest.mark.parametrize("cfg", [NET[5], NET[6], NET[0], GENERAL[0]])
+def test_outputs_are_written_inside_their_bounds_only(cfg):
+    """Guard bands around the cost volume and the input gradients stay untouched (odd sizes: scalar-store and 4-byte
+    staging fallbacks of the tiled kernel; the generic kernel), every element is written."""
+    from acfm_video_3d_reconstruction_b200 import _lib
+    from acfm_video_3d_reconstruction_b200.correlation import out_shape
+    a, b = _inputs(cfg, seed=9)
+    B, C, H, W = cfg[:4]
+    args = cfg[4:]
+    ch, oh, ow = out_shape(H, W, *args)
+    G = 64
+
+    def guarded(numel):
+        buf = torch.full((numel + 2 * G,), 123.0, device="cuda")
+        return buf, buf[G:G + numel]
+
+    bo, out = guarded(B * ch * oh * ow)
+    st = _lib.lib().acfm_correlation_fwd(_lib.ptr(a), _lib.ptr(b), B, C, H, W, *args, _lib.ptr(out), _lib.stream_of(a))
+    _lib.check(st, "acfm_correlation_fwd")
+    g = torch.randn(B * ch * oh * ow, device="cuda")
+    b1, g1 = guarded(a.numel())
+    b2, g2 = guarded(a.numel())
+    st = _lib.lib().acfm_correlation_bwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(g), B, C, H, W, *args, _lib.ptr(g1), _lib.ptr(g2), _lib.stream_of(a))
+    _lib.check(st, "acfm_correlation_bwd")
+    torch.cuda.synchronize()
+    for buf, view in ((bo, out), (b1, g1), (b2, g2)):
+        assert (buf[:G] == 123.0).all() and (buf[-G:] == 123.0).all(), "guard band overwritten"
+        assert (view != 123.0).all()
+    want = cref.correlation(a.double(), b.double(), *args)
+    assert util.rel_err(out.view(want.shape).cpu().numpy(), want.cpu().numpy()) < 1e-5

@@ -336,3 +336,51 @@ def test_backward_with_forward_work_lists_equals_full_grid(monkeypatch):
         grads.append(torch.autograd.grad((mask * g).sum(), x)[0])
     assert grads[0][1].abs().sum() == 0 and grads[0][0].abs().sum() > 0
     assert util.rel_err(grads[0].cpu().numpy(), grads[1].cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("S,K", [(256, 20), (100, 5), (90, 3), (72, 1)])
+def test_outputs_are_written_inside_their_bounds_only(S, K):
+    """Guard bands around every output of acfm_raster_fwd (split path: TMA bulk stores of region rows, runs of regions,
+    plain-store fallbacks) and around the backward's gradient stay untouched; every output element is written."""
+    import ctypes
+    from acfm_video_3d_reconstruction_b200 import _lib
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("bird")
+    N, G = 3, 64                                       # G guard elements on both sides (keeps 16-byte alignment)
+    X, cam = util.synth_verts(v, N, seed=31), util.synth_cams(N, seed=32)
+    cam[1, 1:3] = (3.0, 3.0)
+    ndc = F_.project(torch.from_numpy(X).cuda(), torch.from_numpy(cam).cuda(), 5.0, -1.0, -1.0, F_.EYE_Z).detach().contiguous()
+    faces = torch.from_numpy(f).cuda().contiguous()
+    V, Fn = v.shape[0], f.shape[0]
+
+    def guarded(numel, dtype, poison):
+        buf = torch.full((numel + 2 * G,), poison, dtype=dtype, device="cuda")
+        return buf, buf[G:G + numel]
+
+    frag = N * S * S * K
+    bp, p2f = guarded(frag, torch.int64, -7)
+    bz, zbuf = guarded(frag, torch.float32, 123.0)
+    bd, dists = guarded(frag, torch.float32, 123.0)
+    bm, mask = guarded(N * S * S, torch.float32, 123.0)
+    bv, vis = guarded(N * V, torch.float32, 123.0)
+    nws = int(_lib.lib().acfm_raster_fwd_workspace_bytes(N, S, S))
+    bw, ws = guarded(nws, torch.uint8, 77)
+    soft = K > 1
+    st = _lib.lib().acfm_raster_fwd(_lib.ptr(ndc), _lib.ptr(faces), 1, 0, N, V, Fn, S, S, K, F_.BLUR_SOFT if soft else 0.0, 0, 0,
+                                    F_.SIGMA if soft else 0.0, _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), None,
+                                    _lib.ptr(mask) if soft else None, _lib.ptr(vis), _lib.ptr(ws), nws, _lib.stream_of(ndc))
+    _lib.check(st, "acfm_raster_fwd")
+    torch.cuda.synchronize()
+    for buf, view, poison in ((bp, p2f, -7), (bz, zbuf, 123.0), (bd, dists, 123.0), (bv, vis, 123.0), (bw, ws, 77)) + (((bm, mask, 123.0),) if soft else ()):
+        assert (buf[:G] == poison).all() and (buf[-G:] == poison).all(), "guard band overwritten"
+    assert (p2f != -7).all() and (zbuf != 123.0).all() and (dists != 123.0).all() and (vis != 123.0).all()
+    assert (p2f >= 0).any() and (p2f.view(N, -1)[1] == -1).all()
+    if soft:
+        assert (mask != 123.0).all()
+        bg, g = guarded(N * V * 3, torch.float32, 123.0)
+        gm = torch.ones(N * S * S, device="cuda")
+        st = _lib.lib().acfm_raster_soft_bwd(_lib.ptr(ndc), _lib.ptr(faces), 1, 0, N, V, Fn, S, S, K, F_.SIGMA, _lib.ptr(p2f), _lib.ptr(dists),
+                                             _lib.ptr(mask), _lib.ptr(gm), _lib.ptr(g), _lib.ptr(ws), _lib.stream_of(ndc))
+        _lib.check(st, "acfm_raster_soft_bwd")
+        torch.cuda.synchronize()
+        assert (bg[:G] == 123.0).all() and (bg[-G:] == 123.0).all() and (g != 123.0).all() and g.view(N, -1)[1].abs().sum() == 0
