@@ -7,16 +7,25 @@
 // inside / blur / depth decisions) is computed in strict IEEE fp32 in the CPU reference's operator
 // order, so pix_to_face, zbuf and dists are bit-identical to oracle/.
 //
-// One CTA per (render, 32x32-pixel region):
+// Three kernels per call when the caller passes a workspace (the split path, further down in this file):
+//   raster_prep_kernel   one CTA per render: mesh bounding box -> live regions (filed heaviest first by face count, so
+//                        the rasterizer's grid ends on light regions) and runs of empty regions;
+//   raster_fill_kernel   second stream: the -1 padding of the empty regions (87% of all fragment bytes at the reference's
+//                        workloads) written by the TMA unit with cp.async.bulk shared -> global stores, concurrently;
+//   raster_fwd_kernel    one CTA per LIVE (render, 32x32-pixel region), described below.
+// Without a workspace raster_fwd_kernel runs on every region and pads the empty ones itself.
+//
+// raster_fwd_kernel, one CTA per (render, 32x32-pixel region):
 //   1. the render's vertices (V*12 B) are staged into shared memory by the TMA unit (cp.async.bulk +
-//      mbarrier); a CTA whose region lies outside the blur-expanded bounding box of the mesh takes the
-//      pure fill path at once (~75% of the CTAs of the reference workloads);
+//      mbarrier); without the split path a CTA whose region lies outside the blur-expanded bounding box of
+//      the mesh takes the pure fill path at once (~75% of the regions of the reference workloads);
 //   2. all F faces are culled against the region (face-level skips of §9.4 + blur-expanded bbox),
 //      survivors compacted with warp ballots and bucketed front to back by depth;
 //   3. the first `cap` region faces get a RECORD in shared memory, set up once per region: vertices,
 //      barycentric denominator, the refined reciprocals shared by the exact divisions, and three
 //      conservative edge equations (see below);
-//   4. warps pull 8x4-pixel tiles (one pixel per lane) from a shared counter.  Per tile:
+//   4. warps pull 8x4-pixel tiles (one pixel per lane) from a shared counter, heaviest tile first (faces per tile are
+//      counted while the records are written).  Per tile:
 //      (a) scan, lane = face: tile-vs-bbox and tile-vs-edge-equation culling, one ballot per 32 faces;
 //      (b) filter, lane = pixel, face uniform: exact bbox test + conservative edge test (6 FFMA), the
 //          survivors' record ids are pushed on a per-lane queue;
