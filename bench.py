@@ -543,6 +543,7 @@ def post_optimize_bench(hp, cfg, cpu=True, frames=12, iters=20):
     from acfm_video_3d_reconstruction_b200 import image_utils
     from acfm_video_3d_reconstruction_b200.predictor import PostOptimizer
     d = hp.device
+    frames = min(frames, cfg["frames"])          # cams are hypothesis-major: the first cfg["frames"] rows are hypothesis 0
     masks = hp.h_target[:frames].to(d)
     edts = image_utils.compute_dt_barrier(masks)
     bds = image_utils.compute_boundaries(masks)
