@@ -13,7 +13,10 @@ One "step" = one pass of the hot path over one batch of synthetic input on every
 Workload at N=1 is BASELINE.json configs[1] (C2): bird template 642 v / 1280 f, batch 64 frames x 8 camera
 hypotheses = 512 renders of 256 x 256, K = 20, 32 handles.  Weak scaling: every rank owns its own 64 frames.
 `value` = renders of all ranks / max-over-ranks device time, inputs resident in HBM.  `e2e` = the same through the
-public API with host (pinned) inputs copied in and the loss + gradients copied out inside the timed region.
+public API with host (pinned) inputs copied in and the loss + gradients copied out inside the timed region (step replayed
+from a CUDA graph, the next step's inputs prefetched on a copy stream; `e2e.serial_value` = without the prefetch).
+Side measurements in the same line (N = 1): `target_maps`, `post_optimize`, `correlation` (vs the reference's own extension
+compiled for sm_100a), `gpu_standin`.
 `--impl reference` times the CPU oracle (restated PyTorch3D 0.3.0 CPU algorithm; the real wheel is not installable)
 on the host cores for the same metric.
 """
