@@ -338,6 +338,33 @@ def test_backward_with_forward_work_lists_equals_full_grid(monkeypatch):
     assert util.rel_err(grads[0].cpu().numpy(), grads[1].cpu().numpy()) < 1e-5
 
 
+def test_non_square_image_split_equals_single_kernel():
+    """The C ABI takes H != W (the Python mirror only renders squares): split and single-kernel paths agree byte for byte."""
+    from acfm_video_3d_reconstruction_b200 import _lib
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("horse")
+    N, H, W, K = 3, 96, 200, 8
+    X, cam = util.synth_verts(v, N, seed=41), util.synth_cams(N, seed=42)
+    ndc = F_.project(torch.from_numpy(X).cuda(), torch.from_numpy(cam).cuda(), 5.0, -1.0, -1.0, F_.EYE_Z).detach().contiguous()
+    faces = torch.from_numpy(f).cuda().contiguous()
+    outs = []
+    for use_ws in (True, False):
+        p2f = torch.empty(N, H, W, K, dtype=torch.int64, device="cuda")
+        zbuf, dists = torch.empty(N, H, W, K, device="cuda"), torch.empty(N, H, W, K, device="cuda")
+        mask = torch.empty(N, H, W, device="cuda")
+        nws = int(_lib.lib().acfm_raster_fwd_workspace_bytes(N, H, W)) if use_ws else 0
+        ws = torch.empty(nws, dtype=torch.uint8, device="cuda") if use_ws else None
+        st = _lib.lib().acfm_raster_fwd(_lib.ptr(ndc), _lib.ptr(faces), 1, 0, N, v.shape[0], f.shape[0], H, W, K, F_.BLUR_SOFT, 0, 0, F_.SIGMA,
+                                        _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), None, _lib.ptr(mask), None, _lib.ptr(ws), nws,
+                                        _lib.stream_of(ndc))
+        _lib.check(st, "acfm_raster_fwd")
+        torch.cuda.synchronize()
+        outs.append((p2f, zbuf, dists, mask))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert (outs[0][0] >= 0).any()
+
+
 @pytest.mark.parametrize("S,K", [(256, 20), (100, 5), (90, 3), (72, 1)])
 def test_outputs_are_written_inside_their_bounds_only(S, K):
     """Guard bands around every output of acfm_raster_fwd (split path: TMA bulk stores of region rows, runs of regions,
