@@ -18,11 +18,17 @@ _pi = ctypes.POINTER(ctypes.c_int)
 SIGNATURES = {
     "acfm_version": [],
     "acfm_last_error_string": [],
+    "acfm_set_raster_epsilon": [_c_f],
+    "acfm_get_raster_epsilon": [],
     "acfm_project_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_f, _c_f, _c_vp, _c_vp],
     "acfm_project_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp, _c_vp],
     "acfm_skin_project_fwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_f, _c_f, _c_vp,
                               _c_vp, _c_vp],
     "acfm_skin_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
+    "acfm_handle_solve_workspace_bytes": [_c_int, _c_int],
+    "acfm_handle_solve_fwd": [_c_vp, _c_vp, _c_int, _c_int, ctypes.c_double, _c_vp, _c_vp, _c_i64, _c_vp],
+    "acfm_handle_solve_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_i64, _c_vp],
+    "acfm_handle_solve_singular": [_c_vp, _c_int, _c_int, _c_vp],
     "acfm_softmax_cols_fwd": [_c_vp, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_softmax_cols_bwd": [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_raster_fwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int,
@@ -83,7 +89,8 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = argtypes
             fn.restype = (ctypes.c_char_p if name == "acfm_last_error_string" else
-                          ctypes.c_int64 if name == "acfm_raster_fwd_workspace_bytes" else ctypes.c_int)
+                          ctypes.c_int64 if name in ("acfm_raster_fwd_workspace_bytes", "acfm_handle_solve_workspace_bytes") else
+                          ctypes.c_float if name == "acfm_get_raster_epsilon" else ctypes.c_int)
         _lib = l
     return _lib
 

@@ -3,9 +3,23 @@
 
 #include "common.cuh"
 
+#include <atomic>
+#include <math.h>
+
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<float> g_raster_eps{ACFM_K_EPS_DEFAULT};
 }
+
+float acfm_raster_epsilon() { return g_raster_eps.load(std::memory_order_relaxed); }
+
+extern "C" int acfm_set_raster_epsilon(float eps) {
+  ACFM_REQUIRE(eps >= 0.0f && isfinite(eps), ACFM_ERR_BAD_ARG, "acfm_set_raster_epsilon: eps must be finite and >= 0");
+  g_raster_eps.store(eps, std::memory_order_relaxed);
+  return ACFM_OK;
+}
+
+extern "C" float acfm_get_raster_epsilon(void) { return acfm_raster_epsilon(); }
 
 void acfm_set_error(const char* fmt, ...) {
   va_list ap;

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        -ccbin /usr/bin/g++ --fmad=true -Xptxas -v)
-SRCS=(api.cu project.cu skin.cu camera.cu raster_fwd.cu raster_bwd.cu shade.cu uvsample.cu losses.cu reproj.cu laplacian.cu targets.cu priors.cu correlation.cu)
+SRCS=(api.cu project.cu skin.cu handle_solve.cu camera.cu raster_fwd.cu raster_bwd.cu shade.cu uvsample.cu losses.cu reproj.cu laplacian.cu targets.cu priors.cu correlation.cu)
 OBJS=()
 PIDS=()
 NAMES=()

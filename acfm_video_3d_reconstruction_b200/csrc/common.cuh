@@ -67,7 +67,11 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
-#define ACFM_K_EPS 1e-8f  // PyTorch3D kEpsilon
+// PyTorch3D kEpsilon: 1e-8 in the release the reference pins (0.3.0, as restated); releases before 0.2
+// used 1e-30.  A run-time setting of the rasterizer (acfm_set_raster_epsilon), because the depth order of near-coplanar
+// neighbours is sensitive to it (tests/test_oracle_variants.py) and the value cannot be checked against the upstream source here.
+#define ACFM_K_EPS_DEFAULT 1e-8f
+float acfm_raster_epsilon();  // host: the current setting (api.cu)
 
 // PixToNdc: -1 + (2 i + 1) / S
 __device__ __forceinline__ float pix_to_ndc(int i, int S) {
@@ -77,21 +81,6 @@ __device__ __forceinline__ float pix_to_ndc(int i, int S) {
 // EdgeFunctionForward(p, a, b)
 __device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay, float bx, float by) {
   return fsub(fmul(fsub(px, ax), fsub(by, ay)), fmul(fsub(py, ay), fsub(bx, ax)));
-}
-
-// PointLineDistanceForward(p, a, b): squared distance to segment ab
-__device__ __forceinline__ float point_line_dist(float px, float py, float ax, float ay, float bx, float by) {
-  const float bax = fsub(bx, ax), bay = fsub(by, ay);
-  const float l2 = fadd(fmul(bax, bax), fmul(bay, bay));
-  if (l2 <= ACFM_K_EPS) {
-    const float dx = fsub(px, bx), dy = fsub(py, by);
-    return fadd(fmul(dx, dx), fmul(dy, dy));
-  }
-  const float t = fdiv(fadd(fmul(bax, fsub(px, ax)), fmul(bay, fsub(py, ay))), l2);
-  const float tt = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
-  const float qx = fadd(ax, fmul(tt, bax)), qy = fadd(ay, fmul(tt, bay));
-  const float dx = fsub(px, qx), dy = fsub(py, qy);
-  return fadd(fmul(dx, dx), fmul(dy, dy));
 }
 
 // ---------------------------------------------------------------------------------------------

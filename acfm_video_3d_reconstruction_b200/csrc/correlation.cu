@@ -285,7 +285,11 @@ extern "C" int acfm_correlation_fwd(const float* input1, const float* input2, in
   ACFM_REQUIRE(input1 && input2 && output, ACFM_ERR_BAD_ARG, "acfm_correlation_fwd: null pointer");
   p.in1 = input1; p.in2 = input2; p.out = output;
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool force_generic = getenv("ACFM_CORR_GENERIC") != nullptr;
+#ifdef ACFM_TUNING
+  static const bool force_generic = getenv("ACFM_CORR_GENERIC") != nullptr;  // tuning builds only (scripts/build_variant.sh)
+#else
+  const bool force_generic = false;
+#endif
   if (kernel_size == 1 && stride1 == 1 && stride2 == 1 && p.dr == kDR && B <= 65535 && !force_generic) {
     const dim3 grid((p.outW + kTX - 1) / kTX, (p.outH + kTY - 1) / kTY, B);
     ACFM_REQUIRE(grid.y <= 65535, ACFM_ERR_UNSUPPORTED, "acfm_correlation_fwd: output too tall");

@@ -65,6 +65,7 @@ struct RasterParams {
   long long faces_stride;  // elements between renders (0: shared topology)
   int N, V, F, H, W, K;
   float blur, sq_blur, sigma;
+  float k_eps;  // kEpsilon (acfm_set_raster_epsilon)
   int clip, cull;
   long long* p2f;
   float* zbuf;
@@ -75,15 +76,20 @@ struct RasterParams {
   int regions_x, regions_y;
   int cap;      // face records per region
   int vec_ok;   // output pointers are 16-byte aligned
+  int bulk_ok;  // rows of the fragment tensors are 16-byte aligned: the padding kernel may use bulk stores
+  int pad_balance;  // bytes of padding per live region above which every padding CTA works (else 5/8 of them)
   const int* work;  // split path, written by raster_prep_kernel: {live, fill runs, empty regions, -, live per weight class [4],
                     //   listR[4][N*regions], listF[N*regions][2]}
 };
 
+// slots of the padding pattern: one region row at K, at least 640 (bulk stores below ~2.5 KB reach a third of the HBM write rate)
+__host__ __device__ inline int fill_pattern_slots(int K) { return max(kRegion * K, 640); }
+
 // shared-memory carve-up, identical on host and device
 struct FwdSmem {
   int off_ndc, off_red, off_hist, off_tw, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
-  int w_k, w_d, w_q, w_cnt, w_ord;  // offsets inside one warp's slab
-  int KS;                         // per-lane list stride (odd)
+  int w_z, w_d, w_f, w_o, w_q, w_cnt, w_ord;  // offsets inside one warp's slab
+  int KS;                                     // per-lane row stride in entries
   __host__ __device__ FwdSmem(int V, int F, int K, int nwarps, int cap) {
     int o = 32;  // mbarrier + counters
     off_ndc = o; o += 2 * kRegion * 4;  // pixel-centre NDC coordinates of the region's columns and rows
@@ -97,10 +103,15 @@ struct FwdSmem {
     off_verts = o;
     const int vb = ((V * 12 + 16 + 15) / 16) * 16;
     off_tmp = o + vb;
-    KS = K | 1;
+    // rows of K entries padded to 16 bytes of depth words with an ODD number of 16-byte chunks: a quarter warp's LDS.128
+    // of the same chunk index then falls into 8 distinct bank groups (the rank pass reads the depths four at a time)
+    KS = ((K + 3) / 4) * 4;
+    if (((KS / 4) & 1) == 0) KS += 4;
     int w = 0;
-    w_k = w; w += KS * 32 * 8;
-    w_d = w; w += KS * 32 * 4;
+    w_z = w; w += KS * 32 * 4;   // depth bits
+    w_d = w; w += KS * 32 * 4;   // signed squared distance
+    w_f = w; w += KS * 32 * 2;   // face id (ushort)
+    w_o = w; w += KS * 32;       // slot of the k-th nearest entry (rank pass)
     w_q = w; w += kQueue * 32;
     w_cnt = w; w += 32;
     w_ord = w; w += 32;
@@ -151,7 +162,7 @@ struct FaceB {
 // to local memory on every pair, taken or not.
 constexpr unsigned kNoFragment = 0xffffffffu;
 struct FragZD { unsigned zbits; float sd; };
-__device__ __forceinline__ bool eval_pair_generic_impl(const FaceB& r, float xf, float yf, int clip, float blur, unsigned& zbits, float& sd) {
+__device__ __forceinline__ bool eval_pair_generic_impl(const FaceB& r, float xf, float yf, int clip, float blur, float eps, unsigned& zbits, float& sd) {
   const float dx0 = fsub(xf, r.x0), dy0 = fsub(yf, r.y0), dx1 = fsub(xf, r.x1), dy1 = fsub(yf, r.y1);
   const float dx2 = fsub(xf, r.x2), dy2 = fsub(yf, r.y2);
   const float ex01 = fsub(r.x1, r.x0), ey01 = fsub(r.y1, r.y0), ex02 = fsub(r.x2, r.x0), ey02 = fsub(r.y2, r.y0);
@@ -172,9 +183,9 @@ __device__ __forceinline__ bool eval_pair_generic_impl(const FaceB& r, float xf,
   const float l01 = fadd(fmul(ex01, ex01), fmul(ey01, ey01));
   const float l02 = fadd(fmul(ex02, ex02), fmul(ey02, ey02));
   const float l12 = fadd(fmul(ex12, ex12), fmul(ey12, ey12));
-  const float d01 = point_line_dist_h(dx0, dy0, dx1, dy1, r.x0, r.y0, xf, yf, ex01, ey01, l01, r.r01, r.flags & 0x20000);
-  const float d02 = point_line_dist_h(dx0, dy0, dx2, dy2, r.x0, r.y0, xf, yf, ex02, ey02, l02, r.r02, r.flags & 0x40000);
-  const float d12 = point_line_dist_h(dx1, dy1, dx2, dy2, r.x1, r.y1, xf, yf, ex12, ey12, l12, r.r12, r.flags & 0x80000);
+  const float d01 = point_line_dist_h(dx0, dy0, dx1, dy1, r.x0, r.y0, xf, yf, ex01, ey01, l01, r.r01, r.flags & 0x20000, eps);
+  const float d02 = point_line_dist_h(dx0, dy0, dx2, dy2, r.x0, r.y0, xf, yf, ex02, ey02, l02, r.r02, r.flags & 0x40000, eps);
+  const float d12 = point_line_dist_h(dx1, dy1, dx2, dy2, r.x1, r.y1, xf, yf, ex12, ey12, l12, r.r12, r.flags & 0x80000, eps);
   const float dist = fminf(fminf(d01, d02), d12);
   const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
   if (!inside && dist >= blur) return false;
@@ -184,11 +195,11 @@ __device__ __forceinline__ bool eval_pair_generic_impl(const FaceB& r, float xf,
   return true;
 }
 
-__device__ __noinline__ FragZD eval_pair_generic(FaceB r, float xf, float yf, int clip, float blur) {
+__device__ __noinline__ FragZD eval_pair_generic(FaceB r, float xf, float yf, int clip, float blur, float eps) {
   FragZD o;
   o.zbits = kNoFragment; o.sd = 0.0f;
   unsigned z; float d;
-  if (eval_pair_generic_impl(r, xf, yf, clip, blur, z, d)) { o.zbits = z; o.sd = d; }
+  if (eval_pair_generic_impl(r, xf, yf, clip, blur, eps, z, d)) { o.zbits = z; o.sd = d; }
   return o;
 }
 
@@ -207,9 +218,9 @@ __device__ __forceinline__ float seg_dist_t(float t, float ax, float ay, float b
 // subexpressions shared; edge(p,v2,v0) uses -(v2-v0), whose negation commutes with rounding.
 constexpr int kFaceFast = 0x100000;
 
-__device__ __forceinline__ bool eval_pair(const FaceB& r, float xf, float yf, int clip, float blur, unsigned& zbits, float& sd) {
+__device__ __forceinline__ bool eval_pair(const FaceB& r, float xf, float yf, int clip, float blur, float eps, unsigned& zbits, float& sd) {
   if (!(r.flags & kFaceFast)) {
-    const FragZD o = eval_pair_generic(r, xf, yf, clip, blur);
+    const FragZD o = eval_pair_generic(r, xf, yf, clip, blur, eps);
     zbits = o.zbits; sd = o.sd;
     return o.zbits != kNoFragment;
   }
@@ -267,12 +278,12 @@ struct FaceSetup {
 };
 
 __device__ __forceinline__ void setup_face(FaceSetup& s, int f, float x0, float y0, float z0, float x1, float y1, float z1,
-                                           float x2, float y2, float z2, float blur, float sq_blur) {
+                                           float x2, float y2, float z2, float blur, float sq_blur, float eps) {
   FaceB& b = s.b;
   b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; b.x2 = x2; b.y2 = y2; b.z0 = z0; b.z1 = z1; b.z2 = z2;
   s.bxmin = fsub(fminf(fminf(x0, x1), x2), sq_blur); s.bxmax = fadd(fmaxf(fmaxf(x0, x1), x2), sq_blur);
   s.bymin = fsub(fminf(fminf(y0, y1), y2), sq_blur); s.bymax = fadd(fmaxf(fmaxf(y0, y1), y2), sq_blur);
-  b.den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), ACFM_K_EPS);  // bary denominator
+  b.den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), eps);  // bary denominator
   b.yden = rcp_refined(b.den);
   const float ex01 = fsub(x1, x0), ey01 = fsub(y1, y0), ex02 = fsub(x2, x0), ey02 = fsub(y2, y0);
   const float ex12 = fsub(x2, x1), ey12 = fsub(y2, y1);
@@ -282,7 +293,7 @@ __device__ __forceinline__ void setup_face(FaceSetup& s, int f, float x0, float 
   b.r01 = rcp_refined(l01); b.r02 = rcp_refined(l02); b.r12 = rcp_refined(l12);
   b.flags = f | (div_safe(b.den) ? 0x10000 : 0) | (div_safe(l01) ? 0x20000 : 0) | (div_safe(l02) ? 0x40000 : 0) |
             (div_safe(l12) ? 0x80000 : 0);
-  if ((b.flags & 0xf0000) == 0xf0000 && l01 > ACFM_K_EPS && l02 > ACFM_K_EPS && l12 > ACFM_K_EPS) b.flags |= kFaceFast;
+  if ((b.flags & 0xf0000) == 0xf0000 && l01 > eps && l02 > eps && l12 > eps) b.flags |= kFaceFast;
   // conservative edge equations (approximate arithmetic; see the header comment)
   const float mag = fmaxf(fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fabsf(x2)), fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fabsf(y2)));
   const float T = 1.001f * sq_blur + 1e-5f * (1.0f + mag);
@@ -307,10 +318,132 @@ __device__ __forceinline__ void setup_face(FaceSetup& s, int f, float x0, float 
   }
 }
 
-// sorted insertion of key = (depth bits << 32 | face) with payload sd into the lane's K-nearest list, ascending.
-// Depth and face share one 64-bit shared-memory word so that a shift step is LDS.64 + LDS + compare + STS.64 + STS.
-__device__ __forceinline__ void list_insert(unsigned long long* lk, float* ld, int K, int& cnt, unsigned long long& last,
-                                            unsigned long long key, float sd) {
+// ---- per-pixel K-nearest SET (unsorted) -----------------------------------------------------------------------------
+// Round 1 kept each pixel's fragments as a sorted list and inserted every new one by shifting.  The candidates of one
+// surface layer arrive in an order unrelated to their depth order AT THE PIXEL (neighbouring faces' planes cross along the
+// shared edge), so a mean insertion moved ~5 entries through a dependent LDS -> compare -> STS chain, and a warp waited for
+// its longest shift every round: 36 % of the kernel's samples at 9 of 32 active lanes (profiles/raster_fwd_r04.md;
+// scripts/sim_lanes.py reproduces the 9.7 lanes and shows that no face order or pixel grouping changes it).
+// Now a lane only keeps the SET of its K nearest fragments: append while it has room (three stores, no load); once full, a
+// nearer fragment replaces the farthest entry.  The farthest entry is looked up lazily (`stale`): after a replacement the
+// old farthest key is still an upper bound, so later fragments beyond it are dropped at once and the set is rescanned only
+// when a fragment falls below the bound.  The depth order is established once per tile by rank_entries(), in uniform
+// control flow.  Built for K = KT = 20, the reference's faces_per_pixel (nmr.py:153): straight-line code that holds the 20
+// depths in registers.  Every other K keeps round 1's sorted lists (list_insert below; the rank pass is quadratic in K).
+struct KSet {
+  unsigned* z;          // [KS] depth bits, 0xffffffff beyond cnt
+  float* d;             // [KS]
+  unsigned short* f;    // [KS]
+  int cnt;
+  int far_slot;                 // slot of the farthest entry (full sets; exact unless stale)
+  unsigned long long far_key;   // its key (depth bits << 32 | face), or an upper bound of it when stale
+  bool stale;
+};
+
+__device__ __forceinline__ unsigned umax3(unsigned a, unsigned b, unsigned c) { return max(max(a, b), c); }
+
+// farthest entry of a FULL set (cnt == K = KT): depth first, then the larger face id (lexicographic (pz, f) as the
+// reference's priority queue).  The maximum depth (3-input integer max), then the slots that hold it as a bit mask; more than
+// one bit is a depth tie at the far end (rare), decided by the face ids.  Out of line, arguments and result by value: the
+// caller keeps its set description in registers.  Returns (face, depth bits, slot).
+template <int KT>
+__device__ __noinline__ uint3 kset_rescan(const unsigned* sz, const unsigned short* sf) {
+  static_assert(KT % 4 == 0 && KT <= 32, "whole 16-byte chunks, one mask word");
+  unsigned zmax = 0u, eqm = 0u;
+  uint4 v[KT / 4];
+#pragma unroll
+  for (int c = 0; c < KT / 4; ++c) v[c] = *reinterpret_cast<const uint4*>(sz + 4 * c);
+#pragma unroll
+  for (int c = 0; c < KT / 4; ++c) zmax = umax3(umax3(zmax, v[c].x, v[c].y), v[c].z, v[c].w);
+#pragma unroll
+  for (int c = 0; c < KT / 4; ++c) {  // (compare + predicated OR with an immediate: two instructions per entry)
+    if (v[c].x == zmax) eqm |= 1u << (4 * c);
+    if (v[c].y == zmax) eqm |= 1u << (4 * c + 1);
+    if (v[c].z == zmax) eqm |= 1u << (4 * c + 2);
+    if (v[c].w == zmax) eqm |= 1u << (4 * c + 3);
+  }
+  int slot = __ffs(eqm) - 1;
+  unsigned fmax = sf[slot];
+  eqm &= eqm - 1u;
+  while (eqm) {
+    const int j = __ffs(eqm) - 1;
+    eqm &= eqm - 1u;
+    if (sf[j] > fmax) { fmax = sf[j]; slot = j; }
+  }
+  return make_uint3(fmax, zmax, (unsigned)slot);
+}
+
+template <int KT>
+__device__ __forceinline__ void kset_add(KSet& s, int K, unsigned zb, unsigned face, float sd) {
+  const unsigned long long key = ((unsigned long long)zb << 32) | face;
+  if (s.cnt < K) {
+    const int slot = s.cnt++;
+    s.z[slot] = zb; s.f[slot] = (unsigned short)face; s.d[slot] = sd;
+    s.far_key = 0xffffffffffffffffull;  // full sets start with an unknown farthest entry
+    s.stale = true;
+  } else if (key < s.far_key) {
+    if (s.stale) {
+      const uint3 r = kset_rescan<KT>(s.z, s.f);
+      s.far_key = ((unsigned long long)r.y << 32) | r.x;
+      s.far_slot = (int)r.z;
+      s.stale = false;
+      if (key >= s.far_key) return;
+    }
+    s.z[s.far_slot] = zb; s.f[s.far_slot] = (unsigned short)face; s.d[s.far_slot] = sd;
+    s.stale = true;  // far_key stays as an upper bound of the new farthest key
+  }
+}
+
+// Depth order of every lane's set, all lanes at once: ord[r] = slot of the entry with r nearer entries.  Rank by counting on
+// the 32-bit depths (slots beyond cnt hold 0xffffffff and never count as nearer); equal depths give equal ranks, which shows
+// as a rank sum below cnt (cnt - 1) / 2 — only then the lane repeats the count on the exact (depth, face) keys.
+// cmax = largest cnt of the warp.  No dependent shared-memory chain.
+template <int KT>
+__device__ __forceinline__ void rank_entries(const unsigned* z, const unsigned short* f, unsigned char* ord, int cnt, int cmax) {
+  int rsum = 0;
+  uint4 v[KT / 4];
+#pragma unroll
+  for (int c = 0; c < KT / 4; ++c) v[c] = *reinterpret_cast<const uint4*>(z + 4 * c);
+#pragma unroll 2
+  for (int i = 0; i < cmax; ++i) {
+    const unsigned zi = z[i];  // 0xffffffff for i >= cnt (harmless: the rank is not used)
+    int r = 0;
+#pragma unroll
+    for (int c = 0; c < KT / 4; ++c)
+      r += (int)(v[c].x < zi) + (int)(v[c].y < zi) + (int)(v[c].z < zi) + (int)(v[c].w < zi);
+    if (i < cnt) { ord[r] = (unsigned char)i; rsum += r; }
+  }
+  if (rsum != ((cnt * (cnt - 1)) >> 1)) {
+    // depth ties in this pixel (0.6 % of the covered pixels of the reference templates): entries whose depth is unique keep
+    // their rank; the tied ones are ranked again on the exact (depth, face) keys
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) {
+      const unsigned zi = z[i];
+      int less = 0, same = 0;
+#pragma unroll 1
+      for (int j = 0; j < cnt; j += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(z + j);
+        less += (int)(v.x < zi) + (int)(v.y < zi) + (int)(v.z < zi) + (int)(v.w < zi);
+        same += (int)(v.x == zi) + (int)(v.y == zi) + (int)(v.z == zi) + (int)(v.w == zi);
+      }
+      if (same > 1) {
+        const unsigned fi = f[i];
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) less += (int)(z[j] == zi && f[j] < fi);
+        ord[less] = (unsigned char)i;
+      }
+    }
+  }
+}
+
+// ---- per-pixel K-nearest LIST (sorted), every K but 20 ------------------------------------------------------------------
+// Round 1's structure, kept for the values of K the reference never uses: the same three arrays held in depth order by
+// insertion (two entries per shared-memory round trip, the second speculative: the shift is a chain of dependent
+// LDS -> compare -> STS, latency per entry is what counts).  Measured at 512^2: K = 32 3.3 ms / K = 50 4.8 ms against 5.1 / 5.7 ms
+// for loop versions of the set operations above (their rank pass is quadratic in K).  The rank table is the identity.
+__device__ __forceinline__ void list_insert(unsigned* lz, unsigned short* lf, float* ld, int K, int& cnt, unsigned long long& last,
+                                            unsigned zb, unsigned face, float sd) {
+  const unsigned long long key = ((unsigned long long)zb << 32) | face;
   int pos;
   if (cnt < K) {
     pos = cnt++;
@@ -318,29 +451,62 @@ __device__ __forceinline__ void list_insert(unsigned long long* lk, float* ld, i
     if (key > last) return;  // not nearer than the current K-th
     pos = K - 1;
   }
-  // Two elements per shared-memory round trip: the second pair of loads is speculative.  The shift loop is a chain of
-  // dependent LDS -> compare -> STS and the warp waits for its longest shift, so latency per element is what counts
-  // (measured at C2: 1 element per trip 4.17 ms, 2 per trip 3.89 ms, 3 and 4 per trip 4.12 / 4.16 ms).
   while (pos > 0) {
-    const unsigned long long k1 = lk[pos - 1];
+    const unsigned z1 = lz[pos - 1], f1 = lf[pos - 1];
     const float d1 = ld[pos - 1];
-    const unsigned long long k2 = pos > 1 ? lk[pos - 2] : 0ull;
+    const unsigned z2 = pos > 1 ? lz[pos - 2] : 0u, f2 = pos > 1 ? lf[pos - 2] : 0u;
     const float d2 = pos > 1 ? ld[pos - 2] : 0.0f;
-    if (k1 < key) break;
-    lk[pos] = k1; ld[pos] = d1;
+    if ((((unsigned long long)z1 << 32) | f1) < key) break;
+    lz[pos] = z1; lf[pos] = (unsigned short)f1; ld[pos] = d1;
     --pos;
-    if (pos == 0 || k2 < key) break;
-    lk[pos] = k2; ld[pos] = d2;
+    if (pos == 0 || (((unsigned long long)z2 << 32) | f2) < key) break;
+    lz[pos] = z2; lf[pos] = (unsigned short)f2; ld[pos] = d2;
     --pos;
   }
-  lk[pos] = key; ld[pos] = sd;
-  if (cnt == K) last = lk[K - 1];
+  lz[pos] = zb; lf[pos] = (unsigned short)face; ld[pos] = sd;
+  if (cnt == K) last = ((unsigned long long)lz[K - 1] << 32) | lf[K - 1];
 }
 
-template <int NWARPS, typename IdxT>
-__global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 96) raster_fwd_kernel(const RasterParams p) {
+// one accepted fragment into the lane's set (KT = 20) or list (any other K)
+template <int KT>
+__device__ __forceinline__ void frag_add(KSet& s, int K, unsigned zb, unsigned face, float sd) {
+  if constexpr (KT > 0) kset_add<KT>(s, K, zb, face, sd);
+  else list_insert(s.z, s.f, s.d, K, s.cnt, s.far_key, zb, face, sd);  // far_key holds the K-th key of a full list
+}
+
+// barrier of the rasterizer warps only (named barrier 1): the CTA's extra padding warp never joins it
+template <int NT>
+__device__ __forceinline__ void raster_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
+// stage_bulk_1d() of common.cuh for the rasterizer warps of a CTA that also holds the padding warp: same contract, with the
+// named barrier instead of __syncthreads()
+template <int NT>
+__device__ __forceinline__ const float* raster_stage_verts(unsigned char* buf, const void* src, uint32_t bytes, uint64_t* bar, uint32_t phase) {
+  const uintptr_t s = (uintptr_t)src;
+  const uint32_t mis = (uint32_t)(s & 15u);
+  unsigned char* dst = buf + mis;
+  const uint32_t head = mis ? min(16u - mis, bytes) : 0u;
+  const uint32_t body = (bytes - head) & ~15u;
+  const uint32_t tail = bytes - head - body;
+  if (threadIdx.x == 0 && body) {
+    mbar_expect_tx(bar, body);
+    tma_bulk_g2s(dst + head, (const unsigned char*)src + head, body, bar);
+  }
+  const uint32_t hw = head >> 2, tw = tail >> 2;  // at most 3 + 3 words, through the LSU
+  if (threadIdx.x < hw) ((float*)dst)[threadIdx.x] = ((const float*)src)[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + tw) {
+    const uint32_t o = ((head + body) >> 2) + (threadIdx.x - 32);
+    ((float*)dst)[o] = ((const float*)src)[o];
+  }
+  if (body) mbar_wait(bar, phase);
+  raster_sync<NT>();
+  return (const float*)dst;
+}
+
+// One (render, 32x32 region) unit, executed by the NWARPS rasterizer warps of a CTA (threads 0 .. NWARPS*32-1).
+template <int NWARPS, typename IdxT, int KT>
+__device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char* smem, const int unit) {
   constexpr int NT = NWARPS * 32;
-  extern __shared__ __align__(16) unsigned char smem[];
   const FwdSmem L(p.V, p.F, p.K, NWARPS, p.cap);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   int* rcount = reinterpret_cast<int*>(smem + 8);
@@ -357,37 +523,16 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int regions = p.regions_x * p.regions_y;
-  int unit = blockIdx.x;
-  if (p.work) {
-    // split path: only regions the mesh can touch reach this kernel (the others go to raster_fill_kernel), in four weight
-    // classes, heaviest first (raster_prep_kernel): the grid's last CTAs are light ones, which shortens the kernel's tail
-    const int U = p.N * regions;
-    int cls = 0;
-#pragma unroll
-    for (; cls < kWeightClasses; ++cls) {
-      const int c = p.work[4 + cls];
-      if (unit < c) break;
-      unit -= c;
-    }
-    if (cls == kWeightClasses) return;
-    unit = p.work[8 + cls * U + unit];
-  }
   const int n = unit / regions;
   const int rg = unit - n * regions;
   const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
   const int px1 = min(px0 + kRegion, p.W), py1 = min(py0 + kRegion, p.H);
-  const int K = p.K;
+  const int K = KT > 0 ? KT : p.K;
   const long long fbase = (long long)n * p.faces_stride;
   const float* gverts = p.ndc + (size_t)n * p.V * 3;
 
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-    *rcount = 0;
-    *next_tile = 0;
-  }
-  __syncthreads();
-  const float* sv = stage_bulk_1d(smem + L.off_verts, gverts, (uint32_t)p.V * 12u, bar, 0);
+  // (the mbarrier and the two counters were initialised by the kernel before the roles split)
+  const float* sv = raster_stage_verts<NT>(smem + L.off_verts, gverts, (uint32_t)p.V * 12u, bar, 0);
 
   const float r_xhi = pix_to_ndc(p.W - 1 - px0, p.W), r_xlo = pix_to_ndc(p.W - 1 - (px1 - 1), p.W);
   const float r_yhi = pix_to_ndc(p.H - 1 - py0, p.H), r_ylo = pix_to_ndc(p.H - 1 - (py1 - 1), p.H);
@@ -413,7 +558,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
     }
     if (tid < kZBuckets) hist[tid] = 0;
     if (tid < 32) tw[tid] = 0;
-    __syncthreads();
+    raster_sync<NT>();
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) {
       xmin = fminf(xmin, red[w * 8]); xmax = fmaxf(xmax, red[w * 8 + 1]);
@@ -455,7 +600,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
       const float x2 = sv[i2 * 3], y2 = sv[i2 * 3 + 1], z2 = sv[i2 * 3 + 2];
       const float zmax = fmaxf(fmaxf(z0, z1), z2);
       const float area = edge_fn(x0, y0, x1, y1, x2, y2);
-      const bool skip = (zmax < 0.0f) || (p.cull && area < 0.0f) || (area <= ACFM_K_EPS && area >= -ACFM_K_EPS);
+      const bool skip = (zmax < 0.0f) || (p.cull && area < 0.0f) || (area <= p.k_eps && area >= -p.k_eps);
       const float bxmin = fsub(fminf(fminf(x0, x1), x2), p.sq_blur), bxmax = fadd(fmaxf(fmaxf(x0, x1), x2), p.sq_blur);
       const float bymin = fsub(fminf(fminf(y0, y1), y2), p.sq_blur), bymax = fadd(fmaxf(fmaxf(y0, y1), y2), p.sq_blur);
       keep = !skip && !(r_xlo > bxmax) && !(r_xhi < bxmin) && !(r_ylo > bymax) && !(r_yhi < bymin);
@@ -470,7 +615,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
       atomicAdd(&hist[bucket], 1);
     }
   }
-  __syncthreads();
+  raster_sync<NT>();
   const int nlist = *rcount;
   if (nlist == 0) {
     cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);
@@ -487,12 +632,12 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
     hist[lane * 2] = incl - a - b;
     hist[lane * 2 + 1] = incl - b;
   }
-  __syncthreads();
+  raster_sync<NT>();
   for (int e = tid; e < nlist; e += NT) {
     const int v = tmp[e];
     rlist[atomicAdd(&hist[v >> 16], 1)] = (unsigned short)(v & 0xffff);
   }
-  __syncthreads();
+  raster_sync<NT>();
 
   // ---- 3. per-region face records; faces per tile ----------------------------------------------------------
   // While a face's record is written, its blur-expanded bounding box is tested against the region's 4 x 8 tiles (same
@@ -510,7 +655,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
       const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
       FaceSetup s;
       setup_face(s, f, sv[i0 * 3], sv[i0 * 3 + 1], sv[i0 * 3 + 2], sv[i1 * 3], sv[i1 * 3 + 1], sv[i1 * 3 + 2], sv[i2 * 3],
-                 sv[i2 * 3 + 1], sv[i2 * 3 + 2], p.blur, p.sq_blur);
+                 sv[i2 * 3 + 1], sv[i2 * 3 + 2], p.blur, p.sq_blur, p.k_eps);
       recA[j] = make_float4(s.bxmin, s.bxmax, s.bymin, s.bymax);
       recA[cap + j] = make_float4(s.g[0], s.g[1], s.g[2], s.g[3]);
       recA[2 * cap + j] = make_float4(s.g[4], s.g[5], s.g[6], s.g[7]);
@@ -534,17 +679,22 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
     }
   }
   if (tw_acc) atomicAdd(&tw[lane], tw_acc);
-  __syncthreads();  // the staging scratch (verts, tmp) is dead from here on: the warp slabs alias it
+  raster_sync<NT>();  // the staging scratch (verts, tmp) is dead from here on: the warp slabs alias it
 
   // ---- 4. warps pull 8x4 tiles; no CTA-wide synchronisation from here on ----------------------------
   unsigned char* wslab = smem + L.off_union + warp * L.warp_bytes;
   const int KS = L.KS;
-  unsigned long long* lk = reinterpret_cast<unsigned long long*>(wslab + L.w_k) + lane * KS;
-  float* ld = reinterpret_cast<float*>(wslab + L.w_d) + lane * KS;
+  KSet ks;
+  ks.z = reinterpret_cast<unsigned*>(wslab + L.w_z) + lane * KS;
+  ks.d = reinterpret_cast<float*>(wslab + L.w_d) + lane * KS;
+  ks.f = reinterpret_cast<unsigned short*>(wslab + L.w_f) + lane * KS;
+  unsigned char* ord = wslab + L.w_o + lane * KS;  // [KS] slot of the lane's k-th nearest entry
   unsigned char* queue = wslab + L.w_q;     // [slot][lane]
   unsigned char* cnts = wslab + L.w_cnt;    // [lane]
-  const uint2* wk = reinterpret_cast<const uint2*>(wslab + L.w_k);  // .x = face, .y = depth bits
+  const unsigned* wz = reinterpret_cast<const unsigned*>(wslab + L.w_z);  // the same arrays, pixel-major, for the output pass
   const float* wd = reinterpret_cast<const float*>(wslab + L.w_d);
+  const unsigned short* wf = reinterpret_cast<const unsigned short*>(wslab + L.w_f);
+  const unsigned char* wo = wslab + L.w_o;
   const int tiles_x = (px1 - px0 + kTileW - 1) / kTileW, tiles_y = (py1 - py0 + kTileH - 1) / kTileH;
   const int ntiles = tiles_x * tiles_y;
   const float inv_sigma_neg = p.sigma > 0.0f ? 1.0f / p.sigma : 0.0f;
@@ -578,8 +728,14 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
     const float t_xhi = ndc_x[lx0], t_xlo = ndc_x[lx0 + kTileW - 1];  // table entries past the image edge repeat the last pixel
     const float t_yhi = ndc_y[ly0], t_ylo = ndc_y[ly0 + kTileH - 1];
 
-    int cnt = 0, qn = 0;
-    unsigned long long last = 0ull;
+    int qn = 0;
+    ks.cnt = 0; ks.far_slot = 0; ks.far_key = 0ull; ks.stale = true;
+    // empty set: every depth slot "infinitely far" (rank pass), every rank slot a valid index (output pass)
+    for (int j = 0; j < KS; j += 4) {
+      *reinterpret_cast<uint4*>(ks.z + j) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      // rank table: filled by rank_entries() for the sets; the identity for the sorted lists
+      *reinterpret_cast<unsigned*>(ord + j) = KT > 0 ? 0u : 0x03020100u + 0x04040404u * (unsigned)(j >> 2);
+    }
 
     // (a)-(c): fill the per-lane queues face by face; drain them when one is full or the faces run out (one drain site)
     // a tile that no record's bounding box touches (and no overflow face could) skips the scan: straight to the padding
@@ -636,8 +792,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
           r.r01 = b3.x; r.r02 = b3.y; r.r12 = b3.z;
           unsigned zb;
           float sd;
-          if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd))
-            list_insert(lk, ld, K, cnt, last, ((unsigned long long)zb << 32) | (unsigned)(r.flags & 0xffff), sd);
+          if (eval_pair(r, xf, yf, p.clip, p.blur, p.k_eps, zb, sd)) frag_add<KT>(ks, K, zb, (unsigned)(r.flags & 0xffff), sd);
         }
       }
       qn = 0;
@@ -653,7 +808,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
         const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
         const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
         setup_face(s, f, gverts[i0 * 3], gverts[i0 * 3 + 1], gverts[i0 * 3 + 2], gverts[i1 * 3], gverts[i1 * 3 + 1],
-                   gverts[i1 * 3 + 2], gverts[i2 * 3], gverts[i2 * 3 + 1], gverts[i2 * 3 + 2], p.blur, p.sq_blur);
+                   gverts[i1 * 3 + 2], gverts[i2 * 3], gverts[i2 * 3 + 1], gverts[i2 * 3 + 2], p.blur, p.sq_blur, p.k_eps);
         hit = !(t_xlo > s.bxmax) && !(t_xhi < s.bxmin) && !(t_ylo > s.bymax) && !(t_yhi < s.bymin);
       }
       unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -670,16 +825,16 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
         if (!valid || xf > axmax || xf < axmin || yf > aymax || yf < aymin) continue;
         unsigned zb;
         float sd;
-        if (eval_pair(r, xf, yf, p.clip, p.blur, zb, sd))
-            list_insert(lk, ld, K, cnt, last, ((unsigned long long)zb << 32) | (unsigned)(r.flags & 0xffff), sd);
+        if (eval_pair(r, xf, yf, p.clip, p.blur, p.k_eps, zb, sd)) frag_add<KT>(ks, K, zb, (unsigned)(r.flags & 0xffff), sd);
       }
     }
 
-    // ---- (d) blend, write ------------------------------------------------------------------------------
+    // ---- (d) depth order, blend, write ------------------------------------------------------------------
     const int npx = min(kTileW, p.W - tx0);
     const int nrows = min(kTileH, p.H - ty0);
-    const unsigned any = __ballot_sync(0xffffffffu, cnt > 0);
-    if (any == 0u) {
+    const int cnt = ks.cnt;
+    const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+    if (cmax == 0) {
       for (int row = 0; row < nrows; ++row) {
         const long long pix = ((long long)n * p.H + ty0 + row) * p.W + tx0;
         warp_fill_frag(p, pix * K, npx * K, lane);
@@ -687,10 +842,13 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
       if (p.mask && valid) p.mask[((long long)n * p.H + yi) * p.W + xi] = 0.0f;
       continue;
     }
+    if constexpr (KT > 0) {
+      if (cmax > 1) rank_entries<KT>(ks.z, ks.f, ord, cnt, cmax);  // one entry: ord[0] = 0 from the reset above
+    }
     if (p.vis && cnt > 0) {
       // visible vertices = vertices of the faces that are nearest at some pixel (the fi_maps -> unique -> scatter_ block
       // of bds_loss / optical_flow_loss, loss_utils.py:213-223,432-441): one lane per distinct face of the tile stores
-      const unsigned fv = (unsigned)lk[0];
+      const unsigned fv = ks.f[ord[0]];
       const unsigned peers = __match_any_sync(__activemask(), fv);
       if (__ffs(peers) - 1 == lane) {
         const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
@@ -700,9 +858,10 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
     }
     if (p.mask && valid) {
       float alpha = 1.0f;
-      for (int i = 0; i < cnt; ++i) {
-        const float prob = 1.0f / (1.0f + expf(ld[i] * inv_sigma_neg));
-        alpha *= (1.0f - prob);
+      for (int i = 0; i < cnt; ++i) {  // in depth order, like the reference's product (the bits of the mask do not depend on
+                                       // the order in which the faces were met)
+        // 1 - sigmoid(-d / sigma) = 1 / (1 + exp(-d / sigma)); fast exp / divide: ~2e-7 relative, the mask is held to 1e-5
+        alpha *= __fdividef(1.0f, 1.0f + __expf(-ks.d[ord[i]] * inv_sigma_neg));
       }
       p.mask[((long long)n * p.H + yi) * p.W + xi] = 1.0f - alpha;
     }
@@ -714,6 +873,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
     if (p.vec_ok && (K & 3) == 0) {
       // p2f: two entries (16 B) per store; zbuf / dists: four entries (16 B) per store
       const int P2 = K >> 1, P4 = K >> 2;
+      // 16-bit magics: exact for divisors <= 50 (brute-forced over e < 32 P); P2 <= 32 and P4 <= 16 here
       const unsigned d2 = (65536u + (unsigned)P2 - 1u) / (unsigned)P2, d4 = (65536u + (unsigned)P4 - 1u) / (unsigned)P4;
       for (int e = lane; e < 32 * P2; e += 32) {
         const int pxl = (int)(((unsigned)e * d2) >> 16);
@@ -721,8 +881,10 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
         const int col = pxl & 7, row = pxl >> 3;
         if (col >= npx || row >= nrows) continue;
         const int c = cnts[pxl];
-        const long long a = k < c ? nF + wk[pxl * KS + k].x : -1ll;
-        const long long b = k + 1 < c ? nF + wk[pxl * KS + k + 1].x : -1ll;
+        const int o = pxl * KS;
+        const unsigned so = *reinterpret_cast<const unsigned short*>(wo + o + k);  // two rank slots
+        const long long a = k < c ? nF + wf[o + (so & 0xffu)] : -1ll;
+        const long long b = k + 1 < c ? nF + wf[o + (so >> 8)] : -1ll;
         longlong2 v; v.x = a; v.y = b;
         *reinterpret_cast<longlong2*>(p.p2f + tbase + row * row_stride + col * K + k) = v;
       }
@@ -732,28 +894,32 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
         const int col = pxl & 7, row = pxl >> 3;
         if (col >= npx || row >= nrows) continue;
         const int c = cnts[pxl];
-        const int o = pxl * KS + k;
+        const int o = pxl * KS;
+        const unsigned so = *reinterpret_cast<const unsigned*>(wo + o + k);  // four rank slots
+        const int s0 = o + (so & 0xffu), s1 = o + ((so >> 8) & 0xffu), s2 = o + ((so >> 16) & 0xffu), s3 = o + (so >> 24);
         float4 z, d;
-        z.x = k < c ? __uint_as_float(wk[o].y) : -1.f; d.x = k < c ? wd[o] : -1.f;
-        z.y = k + 1 < c ? __uint_as_float(wk[o + 1].y) : -1.f; d.y = k + 1 < c ? wd[o + 1] : -1.f;
-        z.z = k + 2 < c ? __uint_as_float(wk[o + 2].y) : -1.f; d.z = k + 2 < c ? wd[o + 2] : -1.f;
-        z.w = k + 3 < c ? __uint_as_float(wk[o + 3].y) : -1.f; d.w = k + 3 < c ? wd[o + 3] : -1.f;
+        z.x = k < c ? __uint_as_float(wz[s0]) : -1.f; d.x = k < c ? wd[s0] : -1.f;
+        z.y = k + 1 < c ? __uint_as_float(wz[s1]) : -1.f; d.y = k + 1 < c ? wd[s1] : -1.f;
+        z.z = k + 2 < c ? __uint_as_float(wz[s2]) : -1.f; d.z = k + 2 < c ? wd[s2] : -1.f;
+        z.w = k + 3 < c ? __uint_as_float(wz[s3]) : -1.f; d.w = k + 3 < c ? wd[s3] : -1.f;
         const long long g = tbase + row * row_stride + col * K + k;
         *reinterpret_cast<float4*>(p.zbuf + g) = z;
         *reinterpret_cast<float4*>(p.dists + g) = d;
       }
     } else {
-      const unsigned kdiv = (65536u + (unsigned)K - 1u) / (unsigned)K;  // e / K == (e * kdiv) >> 16 for e < 32K <= 2048
+      // e / K == umulhi(e, ceil(2^32 / K)) for every e < 2^32 / K (brute-forced for K <= 150, e < 32 K); a 16-bit magic is
+      // wrong for K = 51, 56, 60..63
+      const unsigned kdiv = (unsigned)((0x100000000ull + (unsigned long long)K - 1ull) / (unsigned long long)K);
       for (int e = lane; e < 32 * K; e += 32) {
-        const int pxl = (int)(((unsigned)e * kdiv) >> 16);
+        const int pxl = K == 1 ? e : (int)__umulhi((unsigned)e, kdiv);
         const int k = e - pxl * K;
         const int col = pxl & 7, row = pxl >> 3;
         if (col >= npx || row >= nrows) continue;
         const int c = cnts[pxl];
-        const int o = pxl * KS + k;
+        const int o = pxl * KS + wo[pxl * KS + k];
         const long long g = tbase + row * row_stride + col * K + k;
-        p.p2f[g] = k < c ? nF + wk[o].x : -1ll;
-        p.zbuf[g] = k < c ? __uint_as_float(wk[o].y) : -1.f;
+        p.p2f[g] = k < c ? nF + wf[o] : -1ll;
+        p.zbuf[g] = k < c ? __uint_as_float(wz[o]) : -1.f;
         p.dists[g] = k < c ? wd[o] : -1.f;
       }
     }
@@ -767,13 +933,13 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
         if (col >= npx || row >= nrows) continue;
         float b0 = -1.f, b1 = -1.f, b2 = -1.f;
         if (k < cnts[pxl]) {
-          const int fv = (int)wk[pxl * KS + k].x;
+          const int fv = (int)wf[pxl * KS + wo[pxl * KS + k]];
           const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
           const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
           const float x0 = gverts[i0 * 3], y0 = gverts[i0 * 3 + 1], x1 = gverts[i1 * 3], y1 = gverts[i1 * 3 + 1];
           const float x2 = gverts[i2 * 3], y2 = gverts[i2 * 3 + 1];
           const float pxf = ndc_x[lx0 + col], pyf = ndc_y[ly0 + row];
-          const float den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), ACFM_K_EPS);
+          const float den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), p.k_eps);
           b0 = fdiv(edge_fn(pxf, pyf, x1, y1, x2, y2), den);
           b1 = fdiv(edge_fn(pxf, pyf, x2, y2, x0, y0), den);
           b2 = fdiv(edge_fn(pxf, pyf, x0, y0, x1, y1), den);
@@ -792,19 +958,132 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 104 : 9
   }
 }
 
-// choose the CTA size and the record capacity: most resident warps per SM (227 KB shared per SM, 1 KB
-// reserved per CTA), then the largest record table that keeps that residency
+// ---- the two kernels of the split path ----------------------------------------------------------------------------------
+// 87 % of all fragment bytes of the reference's workloads are the -1 padding of regions the mesh cannot touch.  It is written
+// by raster_fill_kernel BESIDE the rasterizer: one-warp CTAs, one per SM, whose stores are issued by the TMA unit
+// (cp.async.bulk shared -> global from a constant pattern in shared memory: one instruction per row piece, so the LSU / MIO
+// queues stay with the co-resident rasterizer CTAs; a CTA of ordinary stores saturates them — measured 4.05-4.23 ms at C2, no
+// better than one kernel doing everything).  The pattern holds max(32 K, 640) fragment slots (7.5 KB up to K = 20): such a
+// CTA fits beside two resident rasterizer CTAs; 5 KB / 2.5 KB pieces reach the HBM write rate with one CTA per SM, 2 KB /
+// 1 KB pieces a third of it.
+//
+// Placement matters more than anything else here: the padding CTAs must sit one per SM.  Round 1 launched the two kernels on
+// two streams (fork / join events, high priority for the padding) and so depended on a launch race: whenever the
+// rasterizer's grid reached the SMs first, the padding CTAs were packed onto the few SMs that freed up first and wrote at
+// those SMs' rate only — 4x to 30x slower, time inversely proportional to the number of padding CTAs (measured at K = 24 and
+// 48 with round 1's build, at every K when the rasterizer used all registers of an SM; profiles/raster_fwd_r05.md).  Now both
+// kernels are launched on the caller's stream and overlap by PROGRAMMATIC DEPENDENT LAUNCH: the padding kernel starts on the
+// idle GPU after raster_prep_kernel (its <= one-wave grid is spread one CTA per SM) and every CTA signals
+// griddepcontrol.launch_dependents at once; the rasterizer kernel, launched with programmatic stream serialization, is
+// dispatched when all of them have — i.e. exactly when the padding CTAs are in place.  The rasterizer does not read what the
+// padding kernel writes, so it never waits for it, except for ONE thread of its last CTA, which executes griddepcontrol.wait
+// before leaving: the rasterizer grid — and with it everything that follows on the stream — completes only after the
+// padding is complete and visible.  No second stream, no events, nothing to pool or to leak.
+constexpr int kFillThreads = 32;
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void bulk_fill_row(void* dst, const void* pat_smem, int slots, int slot_bytes, int chunk) {
+  for (int o = 0; o < slots; o += chunk)
+    bulk_s2g(reinterpret_cast<unsigned char*>(dst) + (size_t)o * slot_bytes, pat_smem, (uint32_t)(min(chunk, slots - o) * slot_bytes));
+}
+
+__global__ void __maxnreg__(40) raster_fill_kernel(const RasterParams p, const int* ws) {  // (few registers: it shares SM sub-partitions with four 112-register rasterizer warps)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // in place: the rasterizer's grid may be dispatched
+  extern __shared__ __align__(128) unsigned char pat[];
+  const int regions = p.regions_x * p.regions_y;
+  const int countF = ws[1];
+  const int* listF = ws + 8 + kWeightClasses * p.N * regions;
+  const int lane = threadIdx.x;
+  const int K = p.K, chunk = fill_pattern_slots(K);
+  long long* pat8 = reinterpret_cast<long long*>(pat);                         // [chunk] int64 -1
+  float* pat4 = reinterpret_cast<float*>(pat + (size_t)chunk * 8);             // [chunk] float -1
+  if (p.bulk_ok) {
+    for (int e = lane; e < chunk; e += kFillThreads) { pat8[e] = -1ll; pat4[e] = -1.0f; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
+    __syncwarp();
+  }
+  // How many CTAs pad: five eighths of the grid (one CTA on most SMs) write ~4 TB/s, enough to finish under the rasterizer at
+  // the reference's workloads and gentler on it than one per SM (C2, 74 / 92 / 110 / 148 CTAs: 2.95 / 2.79 / 2.80 / 2.85 ms);
+  // the rest joins only when the padding would otherwise outlast the rasterizer (sparse views: few live regions, many bytes
+  // to pad).  Estimate: a live region costs the rasterizer ~0.3 us of the GPU (K = 20, reference templates).
+  const long long pad_bytes = (long long)ws[2] * (kRegion * kRegion) * (16ll * K + 4);
+  const bool all_ctas = pad_bytes > (long long)ws[0] * (long long)p.pad_balance;
+  const int nctas = all_ctas ? gridDim.x : max(1, ((int)gridDim.x * 5) >> 3);
+  if ((int)blockIdx.x >= nctas) return;
+  for (int w = blockIdx.x; w < countF; w += nctas) {
+    const int unit = listF[2 * w], run = listF[2 * w + 1];
+    const int n = unit / regions, rg = unit - n * regions;
+    const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
+    const int px1 = min(px0 + run * kRegion, p.W), py1 = min(py0 + kRegion, p.H);
+    const int npx = px1 - px0, row_el = npx * K;
+    if (p.bulk_ok && (row_el & 3) == 0) {
+      if (py0 + lane < py1) {  // lane = pixel row of the run
+        const long long g = (((long long)n * p.H + py0 + lane) * p.W + px0) * K;  // first fragment slot of the row
+        bulk_fill_row(p.p2f + g, pat8, row_el, 8, chunk);
+        bulk_fill_row(p.zbuf + g, pat4, row_el, 4, chunk);
+        bulk_fill_row(p.dists + g, pat4, row_el, 4, chunk);
+        if (p.bary) bulk_fill_row(p.bary + g * 3, pat4, row_el * 3, 4, chunk);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (p.mask)
+        for (int y = py0; y < py1; ++y)
+          for (int x = lane; x < npx; x += kFillThreads) p.mask[((long long)n * p.H + y) * p.W + px0 + x] = 0.0f;
+    } else {
+      cta_fill_rect<1>(p, n, px0, px1, py0, py1, 0, lane);
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the pattern must outlive the reads; writes complete before exit
+}
+
+// One CTA (NWARPS warps) per (render, region) unit.
+template <int NWARPS, typename IdxT, int KT>
+__global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 112 : 112) raster_fwd_kernel(const RasterParams p) {
+  // (112 registers: two 8-warp CTAs leave every SM sub-partition room for one padding warp beside its four rasterizer warps)
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int regions = p.regions_x * p.regions_y;
+  int unit = blockIdx.x;
+  bool live = true;
+  if (p.work) {
+    // split path: only regions the mesh can touch are rendered (the others are padded by raster_fill_kernel), in four weight
+    // classes, heaviest first (raster_prep_kernel): the grid's last CTAs are light ones, which shortens the kernel's tail
+    const int U = p.N * regions;
+    const int c0 = p.work[4], c1 = p.work[5], c2 = p.work[6], c3 = p.work[7];
+    const int cls = unit < c0 ? 0 : (unit < c0 + c1 ? 1 : (unit < c0 + c1 + c2 ? 2 : 3));
+    live = unit < c0 + c1 + c2 + c3;
+    if (live) unit = p.work[8 + cls * U + (unit - (cls > 0 ? c0 : 0) - (cls > 1 ? c1 : 0) - (cls > 2 ? c2 : 0))];
+  }
+  if (live) {
+    if (threadIdx.x == 0) {
+      mbar_init(reinterpret_cast<uint64_t*>(smem), 1);
+      mbar_fence_init();
+      *reinterpret_cast<int*>(smem + 8) = 0;   // rcount
+      *reinterpret_cast<int*>(smem + 12) = 0;  // next_tile
+    }
+    __syncthreads();
+    raster_unit<NWARPS, IdxT, KT>(p, smem, unit);
+  }
+  // the grid completes only after the padding kernel has (see above): one thread of the last CTA waits for it
+  if (p.work && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// choose the CTA size and the record capacity: 8-warp CTAs, two per SM (227 KB shared per SM, 1 KB reserved per CTA), with
+// the largest record table that keeps two resident; 4-warp CTAs when the per-warp sets are too large for that (K > ~40).
+// 10- and 12-warp CTAs were measured slower at every shape of the reference (profiles/README.md) and are not built.
 int fwd_pick_config(int V, int F, int K, int* smem_bytes, int* cap_out) {
   int best_nw = 0, best_score = -1, best_cap = 0, best_smem = 0;
-  for (int nw : {8, 10, 12, 4}) {
+  for (int nw : {8, 4}) {
     for (int cap : {256, 224, 192, 160, 128, 96, 64}) {
       const FwdSmem l(V, F, K, nw, cap);
       if (l.total > 227 * 1024) continue;
       const int ctas = min(32, (228 * 1024) / (l.total + 1024));
       const int warps = min(64, ctas * nw);
       // a record table below ~192 entries overflows on ordinary views (a 32x32 region of the reference
-      // templates sees 130-175 faces, up to ~500), so capacity comes first, then resident warps (capped at 16:
-      // measured on C2, 8-warp CTAs x 2 beat 10 x 2 and 12 x 2), then fewer, larger tables
+      // templates sees 130-175 faces, up to ~500), so capacity comes first, then resident warps (capped at 16), then
+      // fewer, larger tables
       const int score = min(cap, 192) * 10000 + min(warps, 16) * 100 + cap / 32;
       if (score > best_score) { best_score = score; best_nw = nw; best_cap = cap; best_smem = l.total; }
     }
@@ -814,13 +1093,18 @@ int fwd_pick_config(int V, int F, int K, int* smem_bytes, int* cap_out) {
   return best_nw;
 }
 
-template <int NWARPS, typename IdxT>
-int launch_fwd(const RasterParams& p, int smem, int ctas, cudaStream_t st) {
-  auto kern = raster_fwd_kernel<NWARPS, IdxT>;
+template <int NWARPS, typename IdxT, int KT>
+int launch_fwd(const RasterParams& p, int smem, int ctas, bool overlap, cudaStream_t st) {
+  auto kern = raster_fwd_kernel<NWARPS, IdxT, KT>;
   static std::atomic<int> smem_set[kAcfmMaxDevices];
   ACFM_CUDA_OK(acfm_ensure_smem(kern, smem, smem_set));
-  kern<<<ctas, NWARPS * 32, smem, st>>>(p);
-  ACFM_LAUNCH_OK("raster_fwd_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(NWARPS * 32); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = overlap ? 1 : 0;  // overlap: dispatch as soon as the padding kernel's CTAs are in place
+  ACFM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   return ACFM_OK;
 }
 
@@ -940,110 +1224,56 @@ __global__ void __launch_bounds__(kPrepThreads) raster_prep_kernel(const RasterP
   }
 }
 
-// The padding is written by the TMA unit (cp.async.bulk shared -> global) from a constant pattern in shared memory: a CTA
-// of ordinary stores saturates its SM's LSU / MIO queue, which the co-resident rasterizer CTAs need for their K-list
-// traffic (measured: LSU fill beside the rasterizer 4.05-4.23 ms, no better than the single kernel); a bulk store is one
-// instruction per row piece and leaves the LSU alone.  One warp per CTA, lane = pixel row of the run.  The pattern holds
-// max(32 K, 640) fragment slots (7.5 KB up to K = 20), so one such CTA fits beside two resident rasterizer CTAs; measured
-// at C2, 5 KB / 2.5 KB pieces reach the HBM write rate with one CTA per SM, 2 KB / 1 KB pieces only a third of it.
-constexpr int kFillThreads = 32;
-
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-}
-
-__device__ __forceinline__ void bulk_fill_row(void* dst, const void* pat_smem, int slots, int slot_bytes, int chunk) {
-  for (int o = 0; o < slots; o += chunk)
-    bulk_s2g(reinterpret_cast<unsigned char*>(dst) + (size_t)o * slot_bytes, pat_smem, (uint32_t)(min(chunk, slots - o) * slot_bytes));
-}
-
-__host__ __device__ inline int fill_pattern_slots(int K) { return max(kRegion * K, 640); }
-
-__global__ void __launch_bounds__(kFillThreads) raster_fill_kernel(const RasterParams p, const int* ws, int bulk_ok) {
-  extern __shared__ __align__(128) unsigned char pat[];
-  const int regions = p.regions_x * p.regions_y;
-  const int countF = ws[1];
-  const int* listF = ws + 8 + kWeightClasses * p.N * regions;
-  const int lane = threadIdx.x;
-  const int K = p.K, chunk = fill_pattern_slots(K);
-  long long* pat8 = reinterpret_cast<long long*>(pat);                         // [chunk] int64 -1
-  float* pat4 = reinterpret_cast<float*>(pat + (size_t)chunk * 8);             // [chunk] float -1
-  if (bulk_ok) {
-    for (int e = lane; e < chunk; e += kFillThreads) { pat8[e] = -1ll; pat4[e] = -1.0f; }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
-    __syncwarp();
-  }
-  // How many CTAs pad: five eighths of the grid (one CTA on most SMs) write ~4 TB/s, enough to finish under the rasterizer at
-  // the reference's workloads and gentler on it than one per SM (C2, 74 / 92 / 110 / 148 CTAs: 2.95 / 2.79 / 2.80 / 2.85 ms);
-  // the rest joins only when the padding would otherwise outlast the rasterizer (sparse views: few live regions, many bytes
-  // to pad).  Estimate: a live region costs the rasterizer ~0.33 us of the GPU (K = 20, reference templates).
-  const long long pad_bytes = (long long)ws[2] * (kRegion * kRegion) * (16ll * K + 4);
-  const bool all_ctas = pad_bytes > (long long)ws[0] * 1200000ll;
-  const int nctas = all_ctas ? gridDim.x : max(1, ((int)gridDim.x * 5) >> 3);
-  if ((int)blockIdx.x >= nctas) return;
-  for (int w = blockIdx.x; w < countF; w += nctas) {
-    const int unit = listF[2 * w], run = listF[2 * w + 1];
-    const int n = unit / regions, rg = unit - n * regions;
-    const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
-    const int px1 = min(px0 + run * kRegion, p.W), py1 = min(py0 + kRegion, p.H);
-    const int npx = px1 - px0, row_el = npx * K;
-    if (bulk_ok && (row_el & 3) == 0) {
-      if (py0 + lane < py1) {
-        const long long g = (((long long)n * p.H + py0 + lane) * p.W + px0) * K;  // first fragment slot of the row
-        bulk_fill_row(p.p2f + g, pat8, row_el, 8, chunk);
-        bulk_fill_row(p.zbuf + g, pat4, row_el, 4, chunk);
-        bulk_fill_row(p.dists + g, pat4, row_el, 4, chunk);
-        if (p.bary) bulk_fill_row(p.bary + g * 3, pat4, row_el * 3, 4, chunk);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (p.mask)
-        for (int y = py0; y < py1; ++y)
-          for (int x = lane; x < npx; x += kFillThreads) p.mask[((long long)n * p.H + y) * p.W + px0 + x] = 0.0f;
-    } else {
-      cta_fill_rect<1>(p, n, px0, px1, py0, py1, 0, lane);
-    }
-  }
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the pattern must outlive the reads; writes complete before exit
-}
-
-// per-thread, per-device side stream + fork/join events of the split path
-struct ForkJoin {
-  cudaStream_t side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  int sms = 0;
+// Tuning hooks (environment variables) exist only in builds with -DACFM_TUNING (scripts/build_variant.sh); the shipped
+// library reads no environment.  ACFM_FWD_WARPS / ACFM_FWD_CAP override the launch configuration, ACFM_FWD_ONLY=raster|fill
+// launches one of the two kernels only (timing: the outputs are incomplete), ACFM_FILL_CTAS / ACFM_FILL_PER_SM /
+// ACFM_FILL_LSU / ACFM_PAD_BALANCE vary the padding kernel, ACFM_NO_PDL serialises the two kernels.
+struct FwdTuning {
+  int only = 0;  // 'r' / 'f'
+  int fill_per_sm = 1, fill_abs = 0, fill_lsu = 0, no_pdl = 0;
+  int pad_balance = 1200000;
 };
-int fork_join(ForkJoin** out) {
-  static thread_local ForkJoin fj[kAcfmMaxDevices];
+const FwdTuning& fwd_tuning() {
+  static const FwdTuning t = [] {
+    FwdTuning v;
+#ifdef ACFM_TUNING
+    if (const char* e = getenv("ACFM_FWD_ONLY")) v.only = e[0];
+    if (const char* e = getenv("ACFM_FILL_PER_SM")) v.fill_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("ACFM_FILL_CTAS")) v.fill_abs = atoi(e);
+    if (const char* e = getenv("ACFM_PAD_BALANCE")) v.pad_balance = atoi(e);
+    v.fill_lsu = getenv("ACFM_FILL_LSU") != nullptr;
+    v.no_pdl = getenv("ACFM_NO_PDL") != nullptr;
+#endif
+    return v;
+  }();
+  return t;
+}
+int device_sm_count(int* sms) {  // cached per device
+  static std::atomic<int> cache[kAcfmMaxDevices];
   int dev = 0;
   ACFM_CUDA_OK(cudaGetDevice(&dev));
-  ForkJoin& f = fj[dev & (kAcfmMaxDevices - 1)];
-  if (!f.side) {
-    ACFM_CUDA_OK(cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev));
-    ACFM_CUDA_OK(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
-    ACFM_CUDA_OK(cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming));
-    int lo = 0, hi = 0;
-    ACFM_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    // highest priority: the fill kernel's few CTAs (one per SM) must be dispatched BEFORE the rasterizer's grid — the block
-    // scheduler does not start a kernel while an earlier one of the same priority still has CTAs waiting
-    ACFM_CUDA_OK(cudaStreamCreateWithPriority(&f.side, cudaStreamNonBlocking, hi));
+  std::atomic<int>& c = cache[dev & (kAcfmMaxDevices - 1)];
+  int v = c.load(std::memory_order_relaxed);
+  if (v == 0) {
+    ACFM_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    c.store(v, std::memory_order_relaxed);
   }
-  *out = &f;
+  *sms = v;
   return ACFM_OK;
 }
-
-// test / tuning hook: ACFM_FWD_WARPS and ACFM_FWD_CAP override the automatic choice
 int fwd_config(int V, int F, int K, int* smem, int* cap) {
   int nw = fwd_pick_config(V, F, K, smem, cap);
+#ifdef ACFM_TUNING
   const char* ew = getenv("ACFM_FWD_WARPS");
   const char* ec = getenv("ACFM_FWD_CAP");
   if (ew || ec) {
     const int w = ew ? atoi(ew) : nw, c = ec ? atoi(ec) : *cap;
-    if ((w == 4 || w == 8 || w == 10 || w == 12) && c >= 0 && c <= 256) {
+    if ((w == 4 || w == 8) && c >= 0 && c <= 256) {
       const FwdSmem l(V, F, K, w, c);
       if (l.total <= 227 * 1024) { nw = w; *cap = c; *smem = l.total; }
     }
   }
+#endif
   return nw;
 }
 
@@ -1080,6 +1310,7 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   p.N = N; p.V = V; p.F = F; p.H = H; p.W = W; p.K = K;
   p.blur = blur_radius; p.sq_blur = sqrtf(blur_radius); p.sigma = sigma;
   p.clip = clip_bary; p.cull = cull_backfaces;
+  p.k_eps = acfm_raster_epsilon();
   p.p2f = (long long*)pix_to_face; p.zbuf = zbuf; p.dists = dists; p.bary = bary; p.mask = mask; p.vis = visible_verts;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
   p.vec_ok = ((((uintptr_t)pix_to_face) | ((uintptr_t)zbuf) | ((uintptr_t)dists)) & 15u) == 0;
@@ -1092,14 +1323,14 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   ACFM_REQUIRE(ctas < (1ll << 28), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: too many CTAs");
   cudaStream_t st = (cudaStream_t)stream;
   if (visible_verts && V > 0) ACFM_CUDA_OK(cudaMemsetAsync(visible_verts, 0, sizeof(float) * (size_t)N * V, st));
-  // split path (see raster_prep_kernel): needs the caller's scratch; without it everything runs in the one kernel
-  static const char* only = getenv("ACFM_FWD_ONLY");  // timing hook: "raster" / "fill" launches just that half (wrong outputs)
-  ForkJoin* fj = nullptr;
+  // split path (see raster_prep_kernel): needs the caller's scratch; without it the rasterizer kernel pads the empty regions
+  const FwdTuning& tune = fwd_tuning();
+  p.bulk_ok = 0; p.pad_balance = tune.pad_balance;
+  bool overlap = false;
   if (workspace) {
     ACFM_REQUIRE(workspace_bytes >= 32 + 24 * ctas && (((uintptr_t)workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
                  "acfm_raster_fwd: workspace must be 16-byte aligned and hold acfm_raster_fwd_workspace_bytes() = %lld bytes",
                  32 + 24 * ctas);
-    if (fork_join(&fj) != ACFM_OK) return ACFM_ERR_CUDA;
     int* ws = (int*)workspace;
     ACFM_CUDA_OK(cudaMemsetAsync(ws, 0, 32, st));
     const int nreg = p.regions_x * p.regions_y;
@@ -1108,32 +1339,26 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
     else raster_prep_kernel<int><<<N, kPrepThreads, weigh ? nreg * 4 : 0, st>>>(p, ws, weigh);
     ACFM_LAUNCH_OK("raster_prep_kernel");
     p.work = ws;
-    ACFM_CUDA_OK(cudaEventRecord(fj->fork, st));
-    ACFM_CUDA_OK(cudaStreamWaitEvent(fj->side, fj->fork, 0));
-    static const int fill_per_sm = getenv("ACFM_FILL_PER_SM") ? std::max(1, atoi(getenv("ACFM_FILL_PER_SM"))) : 1;
-    static const int fill_abs = getenv("ACFM_FILL_CTAS") ? atoi(getenv("ACFM_FILL_CTAS")) : 0;
-    const int fill_ctas = fill_abs > 0 ? fill_abs : (int)std::min<long long>(ctas, (long long)fj->sms * fill_per_sm);
+    int sms = 0;
+    if (device_sm_count(&sms) != ACFM_OK) return ACFM_ERR_CUDA;
     // bulk stores need 16-byte aligned rows: aligned bases, W*K (and so every row start) a multiple of 4 fragment slots
-    const int bulk_ok = p.vec_ok && (((long long)W * K) & 3) == 0 && (!bary || (((uintptr_t)bary) & 15u) == 0) &&
-                        getenv("ACFM_FILL_LSU") == nullptr;
-    if (!only || only[0] != 'r') raster_fill_kernel<<<fill_ctas, kFillThreads, fill_pattern_slots(K) * 12, fj->side>>>(p, ws, bulk_ok);
-    ACFM_LAUNCH_OK("raster_fill_kernel");
-    ACFM_CUDA_OK(cudaEventRecord(fj->join, fj->side));
+    p.bulk_ok = p.vec_ok && (((long long)W * K) & 3) == 0 && (!bary || (((uintptr_t)bary) & 15u) == 0) && !tune.fill_lsu;
+    // at most one wave, one CTA per SM: all of them are resident (and have signalled) before the rasterizer is dispatched
+    const int fill_ctas = tune.fill_abs > 0 ? tune.fill_abs : (int)std::min<long long>(ctas, (long long)sms * tune.fill_per_sm);
+    if (tune.only != 'r') {
+      raster_fill_kernel<<<fill_ctas, kFillThreads, fill_pattern_slots(K) * 12, st>>>(p, ws);
+      ACFM_LAUNCH_OK("raster_fill_kernel");
+      overlap = !tune.no_pdl;
+    }
   }
   int rc = ACFM_ERR_UNSUPPORTED;
-#define ACFM_FWD_CASE(NW)                                                                                       \
-  case NW:                                                                                                      \
-    rc = faces_i64 ? launch_fwd<NW, long long>(p, smem, (int)ctas, st) : launch_fwd<NW, int>(p, smem, (int)ctas, st); \
-    break
-  switch ((fj && only && only[0] == 'f') ? -1 : nw) {
-    case -1: rc = ACFM_OK; break;
-    ACFM_FWD_CASE(12);
-    ACFM_FWD_CASE(10);
-    ACFM_FWD_CASE(8);
-    ACFM_FWD_CASE(4);
-  }
+#define ACFM_FWD_CASE(NW, KT)                                                                          \
+  rc = faces_i64 ? launch_fwd<NW, long long, KT>(p, smem, (int)ctas, overlap, st) : launch_fwd<NW, int, KT>(p, smem, (int)ctas, overlap, st)
+  if (workspace && tune.only == 'f') rc = ACFM_OK;
+  else if (nw == 8 && K == 20) ACFM_FWD_CASE(8, 20);  // the reference's faces_per_pixel: straight-line set operations
+  else if (nw == 8) ACFM_FWD_CASE(8, 0);
+  else if (nw == 4) ACFM_FWD_CASE(4, 0);
 #undef ACFM_FWD_CASE
-  if (fj) ACFM_CUDA_OK(cudaStreamWaitEvent(st, fj->join, 0));  // join even after a failed launch: the side stream must not dangle
   ACFM_REQUIRE(rc != ACFM_ERR_UNSUPPORTED, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: no launch configuration");
   return rc;
 }

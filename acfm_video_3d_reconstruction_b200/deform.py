@@ -72,13 +72,12 @@ class HandleSolver:
     change unless --symmetric, multiframe/main.py:600-601).
 
     L^T L is then a constant PSD matrix whose null space is the constant vector (L 1 = 0 on a connected mesh), and the only
-    per-step part, lbs lbs^T, has rank K_h.  With P~ = L^T L + (c/V) 1 1^T (full rank; inverted ONCE, in fp64) and
-    U~ = [lbs, 1], S = diag(I, -c/V):   M = P~ + U~ S U~^T  and Woodbury gives
-        M^-1 B = P~^-1 B - (P~^-1 U~) (S^-1 + U~^T P~^-1 U~)^-1 U~^T P~^-1 B,
-    i.e. two (V x V) x (V x K_h+1) fp64 GEMMs and one (K_h+1)^2 solve per step instead of a V x V Cholesky factorisation and
-    two V x V triangular solves (~0.85 ms -> ~0.1 ms at V = 642 on B200).  fp64 keeps the result at the accuracy of the direct
-    fp64 solve (cond(P~) ~ 1e4-1e5); W is returned in fp32.  Differentiable w.r.t. lbs (closed-form backward, as
-    _SkinningMatrix)."""
+    per-step part, lbs lbs^T, has rank K_h.  With P~ = L^T L + (c/V) 1 1^T (full rank; inverted ONCE, here, in fp64) and
+    U~ = [lbs, 1], S = diag(I, -c/V):   M = P~ + U~ S U~^T  and Woodbury gives  W = (P~^-1 U~) C^-1 [:, :K_h],
+    C = S^-1 + U~^T P~^-1 U~.  The per-step part runs in libacfm_b200 (csrc/handle_solve.cu: acfm_handle_solve_fwd / _bwd,
+    fp64, 3 + 5 kernels, deterministic) instead of a V x V Cholesky factorisation and two V x V triangular solves per FRAME in
+    the reference.  fp64 keeps the result at the accuracy of the direct fp64 solve (cond(P~) ~ 1e4-1e5); W is returned in
+    fp32.  Differentiable w.r.t. lbs (closed-form backward)."""
 
     def __init__(self, L):
         Ld = L.detach().double()
@@ -91,31 +90,15 @@ class HandleSolver:
         Pt = P + (self.c / V) * ones.matmul(ones.t())
         null_resid = float(Ld.matmul(ones).abs().max())
         try:
-            self.Pinv = torch.linalg.inv(Pt)
+            self.Pinv = torch.linalg.inv(Pt).contiguous()
             resid = float((self.Pinv.matmul(Pt) - torch.eye(V, dtype=torch.float64, device=L.device)).abs().max())
-            self.ok = bool(torch.isfinite(self.Pinv).all()) and resid < 1e-6 and null_resid < 1e-5
+            self.ok = bool(torch.isfinite(self.Pinv).all()) and resid < 1e-6 and null_resid < 1e-5 and self.c > 0 and L.is_cuda
         except RuntimeError:
             self.ok = False
-        self.ones = ones
-        self._sinv = {}
 
-    def _pieces(self, lbs):
-        U = torch.cat([lbs.detach().double(), self.ones], 1)                  # (V,Kh+1)
-        PU = self.Pinv.matmul(U)
-        K1 = U.shape[1]
-        Sinv = self._sinv.get(K1)
-        if Sinv is None:   # built on the host once per handle count: nothing but launches in the steady state (graph capture)
-            d = torch.ones(K1, dtype=torch.float64)
-            d[-1] = -self.V / self.c
-            Sinv = self._sinv[K1] = torch.diag(d).to(U.device)
-        C = Sinv + U.t().matmul(PU)
-        lu, piv, _ = torch.linalg.lu_factor_ex(C, check_errors=False)   # no host sync: the step stays CUDA-graph capturable
-        return U, PU, (lu, piv)
-
-    def _minv(self, pieces, B):
-        U, PU, (lu, piv) = pieces
-        PB = self.Pinv.matmul(B)
-        return PB - PU.matmul(torch.linalg.lu_solve(lu, piv, U.t().matmul(PB)))
+    def workspace(self, Kh):
+        n = int(_lib.lib().acfm_handle_solve_workspace_bytes(self.V, Kh))
+        return torch.empty((n,), dtype=torch.uint8, device=self.Pinv.device)
 
     def __call__(self, lbs):
         return _SolverMatrix.apply(lbs, self)
@@ -124,19 +107,34 @@ class HandleSolver:
 class _SolverMatrix(torch.autograd.Function):
     @staticmethod
     def forward(ctx, lbs, solver):
-        pieces = solver._pieces(lbs)
-        W = solver._minv(pieces, lbs.detach().double())
-        ctx.solver, ctx.pieces = solver, pieces
-        ctx.save_for_backward(lbs, W)
-        return W.float()
+        _lib.require_cuda(lbs)
+        lbs = F_._f32c(lbs.detach())
+        V, Kh = lbs.shape
+        if V != solver.V:
+            raise ValueError(f"lbs has {V} rows, the solver was built for {solver.V} vertices")
+        ws = solver.workspace(Kh)
+        W = torch.empty((V, Kh), dtype=torch.float32, device=lbs.device)
+        with torch.cuda.device(lbs.device):
+            st = _lib.lib().acfm_handle_solve_fwd(_lib.ptr(solver.Pinv), _lib.ptr(lbs), V, Kh, solver.c / V, _lib.ptr(W),
+                                                  _lib.ptr(ws), ws.numel(), _lib.stream_of(lbs))
+        _lib.check(st, "acfm_handle_solve_fwd")
+        _lib.count(3)
+        ctx.solver, ctx.ws = solver, ws
+        ctx.save_for_backward(lbs)
+        return W
 
     @staticmethod
     def backward(ctx, gW):
-        lbs, W = ctx.saved_tensors
-        Z = ctx.solver._minv(ctx.pieces, gW.double())
-        ld = lbs.double()
-        g = Z - Z.matmul(W.t().matmul(ld)) - W.matmul(Z.t().matmul(ld))
-        return g.float(), None
+        lbs, = ctx.saved_tensors
+        V, Kh = lbs.shape
+        gW = F_._f32c(gW)
+        g = torch.empty_like(lbs)
+        with torch.cuda.device(lbs.device):
+            st = _lib.lib().acfm_handle_solve_bwd(_lib.ptr(ctx.solver.Pinv), _lib.ptr(lbs), _lib.ptr(gW), V, Kh, _lib.ptr(g),
+                                                  _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_of(lbs))
+        _lib.check(st, "acfm_handle_solve_bwd")
+        _lib.count(5)
+        return g, None
 
 
 def skinning_matrix(lbs, L, LtL=None, solver=None):

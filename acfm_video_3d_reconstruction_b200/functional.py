@@ -92,6 +92,14 @@ def project(verts, cams, offset_z=0.0, sx=1.0, sy=1.0, z_add=0.0):
 SPLIT_FILL = os.environ.get("ACFM_SPLIT_FILL", "1") != "0"
 
 
+def set_raster_epsilon(eps=1e-8):
+    """kEpsilon of the rasterizer (PyTorch3D geometry_utils: barycentric denominator + eps, degenerate face / edge tests).
+    1e-8 reproduces the release the reference pins (0.3.0); 1e-30 the releases before 0.2.  Process-wide; returns the old value."""
+    old = float(_lib.lib().acfm_get_raster_epsilon())
+    _lib.check(_lib.lib().acfm_set_raster_epsilon(float(eps)), "acfm_set_raster_epsilon")
+    return old
+
+
 def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycentric_coords=False,
               cull_backfaces=False, sigma=0.0, want_bary=False, want_mask=False, want_vis=False):
     """rasterize_meshes on screen-space verts (no autograd).  Returns dict of pix_to_face / zbuf / dists
@@ -121,7 +129,7 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
                                         float(sigma), _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), _lib.ptr(bary),
                                         _lib.ptr(mask), _lib.ptr(vis), _lib.ptr(ws), ws_bytes, _lib.stream_of(ndc))
     _lib.check(st, "acfm_raster_fwd")
-    _lib.count((3 if ws is not None else 1) + (1 if vis is not None else 0))
+    _lib.count((2 if ws is not None else 1) + (1 if vis is not None else 0))
     if vis is not None:
         p2f._acfm_vis = vis   # picked up by loss_utils.visible_vertices
     if _lib.event_hook is not None:

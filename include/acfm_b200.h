@@ -30,6 +30,14 @@ typedef enum {
 int acfm_version(void);
 const char* acfm_last_error_string(void);
 
+/* kEpsilon of the rasterizer (PyTorch3D csrc/utils/geometry_utils.*: added to the barycentric denominator, threshold of the
+ * degenerate-face and degenerate-edge tests).  Default 1e-8, the value of the release the reference
+ * pins (0.3.0); releases before 0.2 used 1e-30.  Process-wide, read at every acfm_raster_fwd call: set it once at start-up
+ * to the value of the PyTorch3D build whose results must be reproduced bit for bit (the depth order of near-coplanar
+ * neighbouring faces depends on it, tests/test_oracle_variants.py). */
+int acfm_set_raster_epsilon(float eps);
+float acfm_get_raster_epsilon(void);
+
 /* ---------------------------------------------------------------------------------------------
  * Projection.  Replaces geom_utils.orthographic_proj_withz / orthographic_proj / quat_rotate /
  * hamilton_product (multiframe/nnutils/geom_utils.py:48-153) and the view set-up of
@@ -68,6 +76,21 @@ int acfm_skin_project_fwd(const float* mean_v, const float* W, const float* delt
  * (The projection part of the backward is acfm_project_bwd with NB-broadcast verts.) */
 int acfm_skin_bwd(const float* W, const float* delta, const float* grad_pred_v, int NB, int V, int Kh,
                   float* grad_delta, float* grad_W, float* grad_mean_v, void* stream);
+
+/* The skinning matrix itself, W = (L^T L + lbs lbs^T)^-1 lbs, for a Laplacian L that is constant across steps: replaces the
+ * per-frame 642 x 642 factorisations of the reference block (repeat + bmm + torch.cholesky + torch.cholesky_solve,
+ * multiframe/main.py:586-608) by a Woodbury update of Pinv = (L^T L + (c/V) 1 1^T)^-1, which the caller inverts ONCE
+ * (fp64, (V,V) row-major; c = trace(L^T L) / V or any positive constant, passed as c_over_V = c / V).  fp64 arithmetic,
+ * three kernels forward / five backward, deterministic reductions.  lbs (V,Kh) = softmax-over-vertices handle weights.
+ *   fwd: W (V,Kh) fp32.  The workspace (acfm_handle_solve_workspace_bytes, 16-byte aligned) keeps what the backward needs.
+ *   bwd: grad_W (V,Kh) -> grad_lbs (V,Kh), with the workspace the matching fwd call filled.
+ *   acfm_handle_solve_singular: 1 if that fwd call met a vanishing pivot (synchronises; for set-up checks and tests). */
+int64_t acfm_handle_solve_workspace_bytes(int V, int Kh);
+int acfm_handle_solve_fwd(const double* Pinv, const float* lbs, int V, int Kh, double c_over_V, float* W, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+int acfm_handle_solve_bwd(const double* Pinv, const float* lbs, const float* grad_W, int V, int Kh, float* grad_lbs,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int acfm_handle_solve_singular(const void* workspace, int V, int Kh, void* stream);
 
 /* Handle weights: softmax over VERTICES (dim 0) of the (V,Kh) parameter — MeshNet.get_lbs
  * (multiframe/nnutils/mesh_net.py:597-599, monocular/nnutils/mesh_net.py:468-470).  x, y, grads (V,K) row-major. */

@@ -49,6 +49,12 @@ def lib():
     return _lib
 
 
+def set_variant(k_eps=1e-8, zmax_keps=False, tie_cuda=False):
+    """Select a variant of the restated rasterizer (the SURVEY.md §9 items that could not be checked against the upstream
+    source; see raster_oracle.inc).  Process-wide; tests that change it restore the default ()."""
+    lib().acfm_oracle_set_variant(ctypes.c_double(k_eps), ctypes.c_int(int(zmax_keps)), ctypes.c_int(int(tie_cuda)))
+
+
 def max_threads():
     return int(lib().acfm_oracle_max_threads())
 

@@ -14,6 +14,10 @@
 #include <omp.h>
 #endif
 
+/* variants of the restated rasterizer (see raster_oracle.inc); process-wide, set by tests only */
+static int acfm_variant_zmax_keps = 0;
+static int acfm_variant_tie_cuda = 0;
+
 #define REAL float
 #define SFX(x) x##_f32
 #include "raster_oracle.inc"
@@ -27,6 +31,13 @@
 #undef REAL
 #undef SFX
 #undef K_EPS
+
+void acfm_oracle_set_variant(double k_eps, int zmax_keps, int tie_cuda) {
+  k_eps_f32 = (float)k_eps;
+  k_eps_f64 = k_eps;
+  acfm_variant_zmax_keps = zmax_keps;
+  acfm_variant_tie_cuda = tie_cuda;
+}
 
 int acfm_oracle_max_threads(void) {
 #ifdef _OPENMP

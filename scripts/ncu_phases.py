@@ -6,10 +6,10 @@ def find(pat):
         if pat in l: return i
     raise KeyError(pat)
 anchors = [("fill helpers", find("void warp_fill_frag(")), ("eval", find("the exact per-(pixel, face) test")), ("setup_face", find("// Full per-face set-up")),
-           ("insert", find("// sorted insertion of key")), ("prologue+bbox", find("template <int NWARPS, typename IdxT>")),
+           ("insert", find("// ---- per-pixel K-nearest SET")), ("prologue+bbox", find("template <int NWARPS, typename IdxT, int KT>\n__global__".split("\n")[0])),
            ("cull+bucket", find("// ---- 2. cull all faces")), ("records", find("// ---- 3. per-region face records")),
            ("tile head", find("// ---- 4. warps pull")), ("scan", find("// (a) scan")), ("filter", find("// (b) filter")),
-           ("evalloop", find("// (c) evaluate")), ("overflow", find("// overflow: region faces")), ("blend+out", find("// ---- (d) blend")),
+           ("evalloop", find("// (c) evaluate")), ("overflow", find("// overflow: region faces")), ("blend+out", find("// ---- (d) depth order, blend")),
            ("end", find("// choose the CTA size"))]
 acc = {}
 for l in open(sys.argv[1]):

@@ -3,7 +3,7 @@
 box, so tests only ever read the .npz files written here.
 
   python tests/golden/make_golden.py            # everything
-  python tests/golden/make_golden.py reproj      # only the named sections (base | reproj | targets | priors)
+  python tests/golden/make_golden.py reproj      # only the named sections (base | reproj | targets | priors | cameras)
 
 What is pinned to the reference's own code:
   templates.npz   verts/faces of the reference's template meshes (monocular/meshes/bird_aligned.obj,
@@ -19,6 +19,9 @@ What is pinned to the reference's own code:
   priors.npz      nnutils/loss_utils.py: locally_rigid_fn run by the reference's own code on a duck-typed packed Meshes;
                   mesh_laplacian_smoothing(method="cot"): PyTorch3D 0.3.0's few lines restated around the reference's own
                   geom_utils.laplacian_cot (values + fp64 gradients)
+  cameras.npz     multiframe/main.py: mirror_cameras, transform_cameras and the camera-assembly block of ShapeTrainer.forward
+                  (:573-582) EXECUTED from the reference's source text (values + fp64 gradients); the three
+                  pytorch3d.transforms functions the mirror branch calls are restated from the published v0.3.0 code
 What is NOT pinned upstream (PyTorch3D 0.3.0 is not installable: parity unpinned):
   raster_small.npz  fragments / masks / gradients from oracle/ itself — a regression pin of the
                     restated algorithm only.
@@ -249,8 +252,103 @@ def priors():
     np.savez_compressed(os.path.join(HERE, "priors.npz"), **out)
 
 
+# ---- camera multiplex assembly ---------------------------------------------------------------------
+def _pt3d_transforms():
+    """pytorch3d.transforms pieces that mirror_cameras star-imports (multiframe/main.py:37), restated from the published
+    v0.3.0 rotation_conversions.py.  Everything else in this section is the reference's own source."""
+    def standardize_quaternion(q):
+        return torch.where(q[..., 0:1] < 0, -q, q)
+
+    def quaternion_raw_multiply(a, b):
+        aw, ax, ay, az = torch.unbind(a, -1)
+        bw, bx, by, bz = torch.unbind(b, -1)
+        return torch.stack((aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                            aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw), -1)
+
+    def quaternion_multiply(a, b):
+        return standardize_quaternion(quaternion_raw_multiply(a, b))
+
+    def _copysign(a, b):
+        return torch.where((a < 0) != (b < 0), -a, a)
+
+    def _sqrt_positive_part(x):
+        ret = torch.zeros_like(x)
+        ret[x > 0] = torch.sqrt(x[x > 0])
+        return ret
+
+    def matrix_to_quaternion(m):
+        m00, m11, m22 = m[..., 0, 0], m[..., 1, 1], m[..., 2, 2]
+        o0 = 0.5 * _sqrt_positive_part(1 + m00 + m11 + m22)
+        x = 0.5 * _sqrt_positive_part(1 + m00 - m11 - m22)
+        y = 0.5 * _sqrt_positive_part(1 - m00 + m11 - m22)
+        z = 0.5 * _sqrt_positive_part(1 - m00 - m11 + m22)
+        return torch.stack((o0, _copysign(x, m[..., 2, 1] - m[..., 1, 2]), _copysign(y, m[..., 0, 2] - m[..., 2, 0]),
+                            _copysign(z, m[..., 1, 0] - m[..., 0, 1])), -1)
+
+    return dict(standardize_quaternion=standardize_quaternion, quaternion_multiply=quaternion_multiply,
+                matrix_to_quaternion=matrix_to_quaternion)
+
+
+def cameras():
+    """cameras.npz: cam_pred produced by EXECUTING the reference's own lines — the functions mirror_cameras and
+    transform_cameras (multiframe/main.py:113-138, taken out of the module with ast because main.py itself imports absl
+    flags, PyTorch3D, visdom ...) and the assembly block of ShapeTrainer.forward (main.py:573-582, run against stand-in
+    `self` / `opts` objects) — values and fp64 gradients."""
+    import ast
+    import textwrap
+    src = open(os.path.join(REF, "multiframe", "main.py")).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "F": torch.nn.functional}
+    ns.update(_pt3d_transforms())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("mirror_cameras", "transform_cameras"):
+            exec(compile(ast.Module([node], []), "multiframe/main.py", "exec"), ns)
+    lines = src.splitlines()
+    # the `else:` body (plain 7-vector embeddings; every documented command runs without --az_el_cam) and the lines after it
+    q = max(i for i, l in enumerate(lines) if l.strip() == "quats = cameras[..., 3:]")   # the one in forward() (:573)
+    assert lines[q - 1].strip() == "cameras = cameras.reshape(opts.num_guesses, -1, 7)"
+    cat = max(i for i, l in enumerate(lines) if l.strip() == "self.cam_pred = torch.cat([scales, translations, quats_n], dim=2)")
+    last = max(i for i, l in enumerate(lines) if "self.transforms.repeat(opts.num_guesses, 1))" in l)
+    assert q + 4 == cat and last == cat + 5
+    block = textwrap.dedent("\n".join(lines[q - 1:cat])) + "\n" + textwrap.dedent("\n".join(lines[cat:last + 1]))
+    assert "F.relu(opts.scale_lr_decay" in block and "mirror_cameras(" in block and "transform_cameras(" in block
+    gen = torch.Generator().manual_seed(11)
+    G, NB = 8, 6
+    raw = torch.randn(G, NB, 7, generator=gen)
+    raw[0, 0, 0] = -40.0                    # relu clamps the scale
+    raw[1, 2, 3] = -abs(raw[1, 2, 3])       # negative real part: standardize_quaternion flips it under the mirror
+    import hashlib
+    out = {"raw": raw.numpy(), "scale_lr_decay": np.float32(0.05),
+           "block_sha1": np.array(hashlib.sha1(block.encode()).hexdigest())}   # which lines ran (not the lines themselves)
+    w = torch.randn(G * NB, 7, generator=gen)
+    for tag, mirror, tf in (
+            ("plain", torch.zeros(NB), torch.cat([torch.ones(NB, 1), torch.zeros(NB, 3)], 1)),
+            ("affine", torch.zeros(NB), torch.cat([torch.rand(NB, 1, generator=gen) + 0.5, torch.randn(NB, 2, generator=gen) * 0.1,
+                                                  (torch.rand(NB, 1, generator=gen) > 0.4).float()], 1)),
+            ("mirror", (torch.rand(NB, generator=gen) > 0.4).float(),
+             torch.cat([torch.rand(NB, 1, generator=gen) + 0.5, torch.randn(NB, 2, generator=gen) * 0.1,
+                        (torch.rand(NB, 1, generator=gen) > 0.4).float()], 1))):
+        res = {}
+        for dt in (torch.float32, torch.float64):
+            cams = raw.to(dt).clone().requires_grad_(True)
+            me = types.SimpleNamespace(input_imgs=torch.zeros(NB, 3, 8, 8), mirror_flag=mirror.to(dt), transforms=tf.to(dt))
+            opts = types.SimpleNamespace(num_guesses=G, scale_lr_decay=0.05)
+            env = dict(ns, self=me, opts=opts, cameras=cams)
+            exec(block, env)
+            res[dt] = (me.cam_pred, cams)
+        (res[torch.float64][0] * w.double()).sum().backward()
+        out.update({f"{tag}_mirror": mirror.numpy(), f"{tag}_transforms": tf.numpy(),
+                    f"{tag}_cam_pred": res[torch.float32][0].detach().numpy(),
+                    f"{tag}_cam_pred64": res[torch.float64][0].detach().numpy(),
+                    f"{tag}_grad_raw": res[torch.float64][1].grad.numpy()})
+    out["grad_w"] = w.numpy()
+    np.savez_compressed(os.path.join(HERE, "cameras.npz"), **out)
+
+
 def main():
-    sections = set(sys.argv[1:]) or {"base", "reproj", "targets", "priors"}
+    sections = set(sys.argv[1:]) or {"base", "reproj", "targets", "priors", "cameras"}
+    if "cameras" in sections:
+        cameras()
     if "priors" in sections:
         priors()
     if "targets" in sections:

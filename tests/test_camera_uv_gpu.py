@@ -37,6 +37,23 @@ def test_camera_assembly_fwd_bwd():
     assert np.abs(out2.cpu().numpy() - ref2.numpy()).max() < 1e-6
 
 
+@pytest.mark.parametrize("tag", ["plain", "affine", "mirror"])
+def test_camera_assembly_vs_reference_golden(tag):
+    """cameras.npz was produced by executing the reference's own source lines (multiframe/main.py:113-138 and :573-582,
+    tests/golden/make_golden.py::cameras).  `plain` and `affine` involve no third-party code at all; the `mirror` rows also run
+    three pytorch3d.transforms functions restated from the published v0.3.0 code (their result enters with weight 1 only on
+    mirrored frames)."""
+    from acfm_video_3d_reconstruction_b200 import camera
+    g = util.golden("cameras.npz")
+    raw = torch.from_numpy(g["raw"]).cuda().requires_grad_(True)
+    out = camera.assemble_cameras(raw, torch.from_numpy(g[f"{tag}_mirror"]).cuda(), torch.from_numpy(g[f"{tag}_transforms"]).cuda(),
+                                  float(g["scale_lr_decay"]))
+    assert np.abs(out.detach().cpu().numpy() - g[f"{tag}_cam_pred64"]).max() < 1e-6
+    assert np.abs(out.detach().cpu().numpy() - g[f"{tag}_cam_pred"]).max() < 1e-6
+    (out * torch.from_numpy(g["grad_w"]).cuda()).sum().backward()
+    assert util.rel_err(raw.grad.cpu().numpy(), g[f"{tag}_grad_raw"]) < 1e-4
+
+
 def test_uv_sampler_vs_grid_sample():
     from acfm_video_3d_reconstruction_b200 import synthetic, texture
     v, f = util.template("bird")

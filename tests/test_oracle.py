@@ -1,6 +1,7 @@
 """CPU tests: the oracle against the golden vectors generated from the reference, against closed-form
 cases, and its backward against fp64 finite differences (SURVEY.md §4 'test pyramid')."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import pt3d_oracle as orc
@@ -252,3 +253,14 @@ def test_correlation_restatement_closed_form():
     y = torch.roll(x, shifts=(1, 2), dims=(2, 3))
     c = cref.correlation(x, y, 4, 1, 4, 1, 1)[:, :, 4:6, 4:8].mean(dim=(0, 2, 3))
     assert int(c.argmax()) == (1 + 4) * 9 + (2 + 4)
+
+
+@pytest.mark.parametrize("tag", ["plain", "affine", "mirror"])
+def test_camera_assembly_restatement_vs_reference_lines(tag):
+    """oracle/torch_ref.assemble_cameras against cameras.npz, which make_golden.py produced by executing the reference's own
+    mirror_cameras / transform_cameras / assembly lines (multiframe/main.py:113-138, :573-582)."""
+    from oracle import torch_ref
+    g = util.golden("cameras.npz")
+    out = torch_ref.assemble_cameras(torch.from_numpy(g["raw"]).double(), torch.from_numpy(g[f"{tag}_mirror"]).double(),
+                                     torch.from_numpy(g[f"{tag}_transforms"]).double(), float(g["scale_lr_decay"]))
+    assert np.abs(out.numpy() - g[f"{tag}_cam_pred64"]).max() < 1e-12

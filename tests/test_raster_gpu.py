@@ -45,6 +45,30 @@ def _assert_fragments_equal(gpu, ref):
         assert np.all(np.abs(s_g - s_r) <= 1e-5 * np.maximum(s_r, 1e-30))
 
 
+def test_raster_epsilon_setting_vs_oracle_variant():
+    """kEpsilon is a run-time setting of the rasterizer (acfm_set_raster_epsilon): with 1e-30, the value of early PyTorch3D
+    releases, the kernel reproduces the oracle's 1e-30 variant bit for bit — and the two settings do differ
+    (tests/test_oracle_variants.py says where)."""
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("bird")
+    N, S = 3, 128
+    X, cam = util.synth_verts(v, N, seed=51), util.synth_cams(N, seed=52)
+    faces = np.repeat(f[None], N, 0)
+    base = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
+    old = F_.set_raster_epsilon(1e-30)
+    try:
+        assert old == np.float32(1e-8)
+        orc.set_variant(k_eps=1e-30)
+        ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
+        out = _gpu_mask_render(X, faces, cam, S, 5.0)
+    finally:
+        orc.set_variant()
+        F_.set_raster_epsilon(old)
+    _assert_fragments_equal(out, ref)
+    assert (ref["pix_to_face"] != base["pix_to_face"]).any()
+    _assert_fragments_equal(_gpu_mask_render(X, faces, cam, S, 5.0), base)   # and back
+
+
 def test_golden_small():
     g = util.golden("raster_small.npz")
     N = g["X"].shape[0]
@@ -188,18 +212,74 @@ def test_many_random_poses_partly_off_screen():
     assert (ref["pix_to_face"][..., -1] >= 0).any(axis=(1, 2)).sum() >= N // 2
 
 
-@pytest.mark.parametrize("cap,warps", [(64, 8), (96, 4), (256, 12)])
-def test_record_capacity_and_cta_shapes(cap, warps, monkeypatch):
-    """Forcing a small record table sends most region faces through the overflow (face-uniform) path; 4- and 12-warp CTAs
-    are the shapes picked for large K / large meshes.  Results must not depend on either."""
-    monkeypatch.setenv("ACFM_FWD_CAP", str(cap))
-    monkeypatch.setenv("ACFM_FWD_WARPS", str(warps))
+def _launch_threads(N, V, F, S, K):
+    import ctypes
+    from acfm_video_3d_reconstruction_b200 import _lib
+    th = ctypes.c_int(0)
+    _lib.check(_lib.lib().acfm_raster_fwd_launch_info(N, V, F, S, S, K, None, None, ctypes.byref(th)), "launch_info")
+    return th.value
+
+
+@pytest.mark.parametrize("K", [24, 50, 51, 60, 63, 64])
+def test_generic_k(K):
+    """K = 20 runs the straight-line specialisation of the per-pixel sets; every other K the loop version.  K = 51 / 60 / 63
+    are values for which a 16-bit magic division of the scalar output pass was wrong (round-1 advisor finding): every slot
+    of every pixel must be written."""
     v, f = util.template("bird")
-    N, S = 3, 128
+    N, S = 2, 128
+    assert _launch_threads(N, v.shape[0], f.shape[0], S, K) == 256
     X, cam = util.synth_verts(v, N, seed=31), util.synth_cams(N, seed=32)
+    cam[:, 0] *= 0.6   # smaller on screen: more faces per pixel, the deep lists fill up
     faces = np.repeat(f[None], N, 0)
-    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
-    out = _gpu_mask_render(X, faces, cam, S, 5.0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0, K=K)
+    out = _gpu_mask_render(X, faces, cam, S, 5.0, K=K)
+    _assert_fragments_equal(out, ref)
+    assert (ref["pix_to_face"][..., -1] >= 0).any()
+
+
+def test_four_warp_ctas_on_a_large_mesh():
+    """A mesh with 8192 faces at K = 64 leaves no room for eight warps' sets beside the region face list: the library falls
+    back to 4-warp CTAs (the only shape besides 8 warps that is built).  Same results."""
+    n = 64
+    gy, gx = np.meshgrid(np.linspace(-0.8, 0.8, n + 1), np.linspace(-0.8, 0.8, n + 1), indexing="ij")
+    rng = np.random.default_rng(3)
+    z = 3.0 + 0.3 * np.sin(3 * gx) * np.cos(2 * gy) + 0.01 * rng.standard_normal(gx.shape)
+    ndc = np.stack([gx, gy, z], -1).reshape(1, -1, 3).astype(np.float32)
+    ndc[..., :2] += (0.004 * rng.standard_normal(ndc[..., :2].shape)).astype(np.float32)
+    idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    faces = np.concatenate([np.stack([a, b, c], 1), np.stack([b, d, c], 1)])[None].astype(np.int64)
+    S, K, blur = 64, 64, 1.5e-2
+    assert faces.shape[1] == 8192 and _launch_threads(1, ndc.shape[1], 8192, S, K) == 128
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    ref = orc.rasterize(ndc, faces, S, blur, K, want_bary=False)
+    mask, p2f, zb, di = F_.soft_silhouette(torch.from_numpy(ndc).cuda(), torch.from_numpy(faces).cuda(), S, blur, K, 1e-3)
+    _assert_fragments_equal(dict(pix_to_face=p2f, zbuf=zb, dists=di), ref)
+    assert (ref["pix_to_face"][..., -1] >= 0).mean() > 0.05   # the 64-deep sets do fill up
+
+
+def test_misaligned_outputs_take_the_scalar_path():
+    """Output tensors that are not 16-byte aligned (a caller's view into a larger buffer) go through the scalar output pass."""
+    from acfm_video_3d_reconstruction_b200 import _lib
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("bird")
+    N, S, K = 2, 64, 20
+    X, cam = util.synth_verts(v, N, seed=41), util.synth_cams(N, seed=42)
+    faces = np.repeat(f[None], N, 0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0, K=K)
+    ndc = torch.from_numpy(ref["ndc"]).cuda()
+    fc = torch.from_numpy(faces).cuda()
+    n = N * S * S * K
+    p2f = torch.full((n + 1,), 7, dtype=torch.int64, device="cuda")[1:]          # 8-byte aligned only
+    zb = torch.full((n + 1,), 7.0, dtype=torch.float32, device="cuda")[1:]       # 4-byte aligned only
+    di = torch.full((n + 1,), 7.0, dtype=torch.float32, device="cuda")[1:]
+    mask = torch.empty((N, S, S), dtype=torch.float32, device="cuda")
+    assert p2f.data_ptr() % 16 != 0 and zb.data_ptr() % 16 != 0
+    st = _lib.lib().acfm_raster_fwd(_lib.ptr(ndc), _lib.ptr(fc), 1, fc.shape[1] * 3, N, ndc.shape[1], fc.shape[1], S, S, K,
+                                    float(F_.BLUR_SOFT), 0, 0, float(F_.SIGMA), _lib.ptr(p2f), _lib.ptr(zb), _lib.ptr(di), None,
+                                    _lib.ptr(mask), None, None, 0, _lib.stream_of(ndc))
+    _lib.check(st, "acfm_raster_fwd")
+    out = dict(pix_to_face=p2f.view(N, S, S, K), zbuf=zb.view(N, S, S, K), dists=di.view(N, S, S, K), mask=mask)
     _assert_fragments_equal(out, ref)
 
 
