@@ -318,7 +318,7 @@ def cameras():
     raw[0, 0, 0] = -40.0                    # relu clamps the scale
     raw[1, 2, 3] = -abs(raw[1, 2, 3])       # negative real part: standardize_quaternion flips it under the mirror
     import hashlib
-    out = {"raw": raw.numpy(), "scale_lr_decay": np.float32(0.05),
+    out = {"raw": raw.numpy(), "scale_lr_decay": np.float64(0.05),
            "block_sha1": np.array(hashlib.sha1(block.encode()).hexdigest())}   # which lines ran (not the lines themselves)
     w = torch.randn(G * NB, 7, generator=gen)
     for tag, mirror, tf in (
