@@ -218,7 +218,10 @@ __device__ __forceinline__ float seg_dist_t(float t, float ax, float ay, float b
 // subexpressions shared; edge(p,v2,v0) uses -(v2-v0), whose negation commutes with rounding.
 constexpr int kFaceFast = 0x100000;
 
-__device__ __forceinline__ bool eval_pair(const FaceB& r, float xf, float yf, int clip, float blur, float eps, unsigned& zbits, float& sd) {
+// far_hi: depth bits beyond which a fragment cannot enter the lane's full set / list any more (0xffffffff while it has room):
+// such pairs leave right after the depth, before the three point-segment distances (60 % of the arithmetic) — a round in which
+// every lane holds such a pair, 19 % of the rounds at C2 (back layers met after the sets are full), skips them altogether.
+__device__ __forceinline__ bool eval_pair(const FaceB& r, float xf, float yf, int clip, float blur, float eps, unsigned far_hi, unsigned& zbits, float& sd) {
   if (!(r.flags & kFaceFast)) {
     const FragZD o = eval_pair_generic(r, xf, yf, clip, blur, eps);
     zbits = o.zbits; sd = o.sd;
@@ -246,6 +249,7 @@ __device__ __forceinline__ bool eval_pair(const FaceB& r, float xf, float yf, in
   }
   float pz = fadd(fadd(fmul(c0w, r.z0), fmul(c1w, r.z1)), fmul(c2w, r.z2));
   if (pz < 0.0f) return false;
+  if (__float_as_uint(pz + 0.0f) > far_hi) return false;  // (ties go on: the face id decides)
   const float l01 = fadd(fmul(ex01, ex01), fmul(ey01, ey01));
   const float l02 = fadd(fmul(ex02, ex02), fmul(ey02, ey02));
   const float l12 = fadd(fmul(ex12, ex12), fmul(ey12, ey12));
@@ -729,7 +733,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
     const float t_yhi = ndc_y[ly0], t_ylo = ndc_y[ly0 + kTileH - 1];
 
     int qn = 0;
-    ks.cnt = 0; ks.far_slot = 0; ks.far_key = 0ull; ks.stale = true;
+    ks.cnt = 0; ks.far_slot = 0; ks.far_key = 0xffffffffffffffffull; ks.stale = true;  // (room: nothing is too far)
     // empty set: every depth slot "infinitely far" (rank pass), every rank slot a valid index (output pass)
     for (int j = 0; j < KS; j += 4) {
       *reinterpret_cast<uint4*>(ks.z + j) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -792,7 +796,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
           r.r01 = b3.x; r.r02 = b3.y; r.r12 = b3.z;
           unsigned zb;
           float sd;
-          if (eval_pair(r, xf, yf, p.clip, p.blur, p.k_eps, zb, sd)) frag_add<KT>(ks, K, zb, (unsigned)(r.flags & 0xffff), sd);
+          if (eval_pair(r, xf, yf, p.clip, p.blur, p.k_eps, (unsigned)(ks.far_key >> 32), zb, sd)) frag_add<KT>(ks, K, zb, (unsigned)(r.flags & 0xffff), sd);
         }
       }
       qn = 0;
@@ -825,7 +829,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         if (!valid || xf > axmax || xf < axmin || yf > aymax || yf < aymin) continue;
         unsigned zb;
         float sd;
-        if (eval_pair(r, xf, yf, p.clip, p.blur, p.k_eps, zb, sd)) frag_add<KT>(ks, K, zb, (unsigned)(r.flags & 0xffff), sd);
+        if (eval_pair(r, xf, yf, p.clip, p.blur, p.k_eps, (unsigned)(ks.far_key >> 32), zb, sd)) frag_add<KT>(ks, K, zb, (unsigned)(r.flags & 0xffff), sd);
       }
     }
 

@@ -91,6 +91,40 @@ def test_handle_solver_matches_direct_solve():
                           deform.skinning_matrix(lbs.cuda(), torch.eye(L.shape[0], device="cuda")))
 
 
+@pytest.mark.parametrize("name,Kh", [("bird", 16), ("horse", 64), ("ico4", 8)])
+def test_handle_solve_kernels_other_sizes(name, Kh):
+    """acfm_handle_solve_fwd / _bwd (csrc/handle_solve.cu) at the reference's other handle counts (16 / 64) and on the
+    2562-vertex template: against the fp64 direct solve; two calls give bit-identical results (deterministic reductions);
+    the pivot check reports a regular system."""
+    from acfm_video_3d_reconstruction_b200 import _lib, deform, synthetic
+    wl = synthetic.Workload(name, frames=1, G=1, handles=Kh, seed=3)
+    lbs = torch.softmax(wl.lbs_param, dim=0)
+    L = wl.L.cuda()
+    solver = deform.HandleSolver(L)
+    assert solver.ok
+    g = torch.randn(lbs.shape, generator=torch.Generator().manual_seed(1))
+    outs = []
+    for _ in range(2):
+        lc = lbs.cuda().requires_grad_(True)
+        W = solver(lc)
+        (W * g.cuda()).sum().backward()
+        outs.append((W.detach().clone(), lc.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ld = lbs.double().requires_grad_(True)
+    M = wl.L.double().t() @ wl.L.double() + ld @ ld.t()
+    W64 = torch.cholesky_solve(ld, torch.linalg.cholesky(M))
+    (W64 * g.double()).sum().backward()
+    assert util.rel_err(outs[0][0].cpu().numpy(), W64.detach().numpy()) < 1e-6
+    assert util.rel_err(outs[0][1].cpu().numpy(), ld.grad.numpy()) < 1e-5
+    ws = solver.workspace(Kh)
+    Wt = torch.empty(lbs.shape, device="cuda")
+    lc = lbs.cuda().contiguous()
+    _lib.check(_lib.lib().acfm_handle_solve_fwd(_lib.ptr(solver.Pinv), _lib.ptr(lc), lc.shape[0], Kh, solver.c / solver.V, _lib.ptr(Wt),
+                                                _lib.ptr(ws), ws.numel(), _lib.stream_of(lc)), "acfm_handle_solve_fwd")
+    assert _lib.lib().acfm_handle_solve_singular(_lib.ptr(ws), lc.shape[0], Kh, _lib.stream_of(lc)) == 0
+    assert torch.equal(Wt, outs[0][0])
+
+
 def test_get_lbs_softmax_over_vertices():
     from acfm_video_3d_reconstruction_b200 import deform
     gen = torch.Generator().manual_seed(2)
