@@ -26,7 +26,7 @@ SIGNATURES = {
                               _c_vp, _c_vp],
     "acfm_skin_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_handle_solve_workspace_bytes": [_c_int, _c_int],
-    "acfm_handle_solve_fwd": [_c_vp, _c_vp, _c_int, _c_int, ctypes.c_double, _c_vp, _c_vp, _c_i64, _c_vp],
+    "acfm_handle_solve_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, ctypes.c_double, _c_vp, _c_vp, _c_i64, _c_vp],
     "acfm_handle_solve_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_i64, _c_vp],
     "acfm_handle_solve_singular": [_c_vp, _c_int, _c_int, _c_vp],
     "acfm_softmax_cols_fwd": [_c_vp, _c_int, _c_int, _c_vp, _c_vp],
@@ -34,6 +34,11 @@ SIGNATURES = {
     "acfm_raster_fwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int,
                         _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "acfm_raster_fwd_workspace_bytes": [_c_int, _c_int, _c_int],
+    "acfm_raster_loss_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
+    "acfm_raster_fwd_losses": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp,
+                               _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp],
+    "acfm_raster_soft_bwd_losses": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp, _c_vp,
+                                    _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp],
     "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_dists_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,
@@ -89,10 +94,35 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = argtypes
             fn.restype = (ctypes.c_char_p if name == "acfm_last_error_string" else
-                          ctypes.c_int64 if name in ("acfm_raster_fwd_workspace_bytes", "acfm_handle_solve_workspace_bytes") else
+                          ctypes.c_int64 if name in ("acfm_raster_fwd_workspace_bytes", "acfm_handle_solve_workspace_bytes",
+                                                    "acfm_raster_loss_workspace_bytes") else
                           ctypes.c_float if name == "acfm_get_raster_epsilon" else ctypes.c_int)
+        if os.environ.get("ACFM_NVTX", "0") not in ("", "0"):
+            l = _NvtxLib(l)   # every C-ABI call becomes an NVTX range named after the entry point (nsys / ncu --nvtx)
         _lib = l
     return _lib
+
+
+class _NvtxLib:
+    """Wraps the CDLL so that each entry point runs inside an NVTX range (ACFM_NVTX=1): the kernels of one call group under
+    its name in a timeline, e.g. acfm_raster_fwd = prep + padding + rasterizer.  Off by default: two extra Python calls per launch."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if not name.startswith("acfm_") or name in ("acfm_last_error_string", "acfm_version"):
+            return fn
+
+        def ranged(*args):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*args)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        setattr(self, name, ranged)
+        return ranged
 
 
 def check(status, what):

@@ -16,9 +16,10 @@ namespace {
 // at the same depth rank) touch different vertices at the same time.  Shared-memory FLOAT atomics are CAS spin
 // loops on sm_100 (ATOMS.CAST.SPIN) while 32-bit INTEGER adds are native fire-and-forget ATOMS.ADD, so the silhouette
 // path accumulates in fixed point: a per-CTA power-of-two scale is derived from the largest |grad_mask| of the
-// region (every contribution with |q - p| <= kRmax is then bounded by 2^27), and each contribution is split into a
-// signed high part and a 12-bit low part added to two int32 accumulators — exact to 2^-27 of the bound, with room
-// for 2^19 additions, and independent of the order of the additions.  The rare contribution beyond the bound (a
+// region (every contribution with |q - p| <= kRmax is then bounded by 2^24), and each contribution is split into a
+// signed high part (|.| <= 2^12) and a 12-bit low part added to two int32 accumulators — exact to 2^-24 of the bound and
+// independent of the order of the additions.  Headroom: the low plane takes 2^18 additions (4095 * 2^18 < 2^31), the high
+// plane 2^19; one CTA adds at most 1024 pixels x K <= 64 fragments = 2^16 contributions to one vertex component.  The rare contribution beyond the bound (a
 // face larger than kRmax on screen) goes straight to global memory as a float atomic.  Gradients reach HBM as one
 // atomicAdd per touched (CTA, vertex, component) instead of PyTorch3D's 4-9 global atomics per fragment.
 // ---------------------------------------------------------------------------------------------
@@ -31,7 +32,12 @@ struct BwdParams {
   const long long* p2f;
   const float* dists;
   const float* mask;
-  const float* grad_mask;
+  const float* grad_mask;   // d loss / d mask (N,H,W), or NULL when everything comes through grad_sums
+  // fused silhouette losses: d loss / d (the four per-render sums of acfm_raster_fwd_losses), targets at render n % NB
+  const float* grad_sums;   // (N,4) or NULL
+  const float* loss_target; // (NB,H,W)
+  const float* loss_edt;    // (NB,H,W) or NULL
+  int NB;
   const float* grad_dists;  // FROM_MASK == false: upstream gradient per fragment (N,H,W,K)
   float* grad_ndc;
   int regions_x, regions_y;
@@ -105,6 +111,21 @@ __device__ __forceinline__ void frag_grad(float px, float py, float x0, float y0
   acc.add(ib * 2 + 1, t * gy, in_range);
 }
 
+// d loss / d mask at one pixel: the caller's grad_mask and / or the backward of the fused per-render sums
+// { sum|m-t|, sum m t, sum (m+t-mt), sum edt m } (losses.cu: mask_sums_bwd_kernel has the same expression), so that a loss
+// computed by acfm_raster_fwd_losses never materialises grad_mask.
+__device__ __forceinline__ float upstream_grad(const BwdParams& p, int n, long long pix, int x, int y, float m) {
+  float g = p.grad_mask ? p.grad_mask[pix] : 0.0f;
+  if (p.grad_sums) {
+    const float* gs = p.grad_sums + (size_t)n * 4;
+    const size_t ti = ((size_t)(n % p.NB) * p.H + y) * p.W + x;
+    const float t = p.loss_target[ti], d = m - t;
+    g += gs[0] * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + gs[1] * t + gs[2] * (1.f - t);
+    if (p.loss_edt) g += gs[3] * p.loss_edt[ti];
+  }
+  return g;
+}
+
 // FROM_MASK: the upstream gradient is d loss / d mask and the blend backward (§9.5) is fused in;
 // otherwise it is d loss / d dists per fragment (texture branch, general rasterize_meshes backward on dists).
 template <typename IdxT, bool FROM_MASK>
@@ -154,8 +175,9 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
     if (x < p.W && y < p.H) {
       const long long pix = ((long long)n * p.H + y) * p.W + x;
       if (FROM_MASK) {
-        gabs = fabsf(p.grad_mask[pix]);
-        act = (p.mask[pix] != 0.0f) && (gabs != 0.0f) && (gabs <= 3.0e38f);  // NaN / inf upstream gradients are dropped
+        const float mv = p.mask[pix];
+        gabs = mv != 0.0f ? fabsf(upstream_grad(p, n, pix, x, y, mv)) : 0.0f;
+        act = (mv != 0.0f) && (gabs != 0.0f) && (gabs <= 3.0e38f);  // NaN / inf upstream gradients are dropped
         if (!act) gabs = 0.0f;
       } else {
         act = p.p2f[pix * K] >= 0;
@@ -192,12 +214,12 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   const float inv_w = 1.0f / (float)p.W, inv_h = 1.0f / (float)p.H;
   float* gout = p.grad_ndc + (size_t)n * p.V * 3;
   // |contribution| <= |grad_mask| / sigma * 2 |q - p| (alpha, prob, t <= 1)  =>  bound = gmax / sigma * 2 kRmax, rounded up
-  // to a power of two; scale maps the bound to 2^27
+  // to a power of two; scale maps the bound to 2^24
   float fx_scale = 1.0f;
   if (FROM_MASK) {
     int e;
-    frexpf(__uint_as_float(*gmax_bits) * inv_sigma * (2.0f * kRmax), &e);  // bound < 2^e
-    fx_scale = ldexpf(1.0f, 27 - e);
+    frexpf(__uint_as_float(*gmax_bits) * inv_sigma * (2.0f * kRmax), &e);  // bound < 2^e (gmax is finite and > 0 here)
+    fx_scale = ldexpf(1.0f, 24 - max(e, -100));  // (clamped: a vanishing bound must not push the scale to infinity)
   }
   const AccFixed accx{acc_hi, acc_lo, fx_scale, gout};
   const AccFloat accl{accf};
@@ -222,7 +244,8 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
     // forward already formed (its rounding only matters where the product, hence the gradient, is < 1e-7 of the largest)
     float ga = 1.0f;
     if (FROM_MASK) {
-      ga = -p.grad_mask[pix] * (1.0f - p.mask[pix]) * inv_sigma;
+      const float mv = p.mask[pix];
+      ga = -upstream_grad(p, n, pix, xi, yi, mv) * (1.0f - mv) * inv_sigma;
       if (ga == 0.0f) continue;
     }
     if (vec) {
@@ -283,13 +306,15 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
 namespace {
 int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                int N, int V, int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
-               const float* mask, const float* grad_mask, const float* grad_dists, float* grad_ndc, const void* work, void* stream) {
+               const float* mask, const float* grad_mask, const float* grad_dists, float* grad_ndc, const void* work, void* stream,
+               const float* grad_sums = nullptr, const float* loss_target = nullptr, const float* loss_edt = nullptr, int NB = 1) {
   ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0 && K >= 1, ACFM_ERR_BAD_ARG, "%s: bad sizes", who);
   ACFM_REQUIRE(!from_mask || sigma > 0.0f, ACFM_ERR_BAD_ARG, "%s: sigma must be > 0", who);
   ACFM_REQUIRE(faces_batch_stride == 0 || faces_batch_stride == (int64_t)F * 3, ACFM_ERR_BAD_ARG, "%s: faces_batch_stride must be 0 or F*3", who);
   if (N == 0 || V == 0) return ACFM_OK;
   ACFM_REQUIRE(ndc && faces && pix_to_face && dists && grad_ndc, ACFM_ERR_BAD_ARG, "%s: null pointer", who);
-  ACFM_REQUIRE(from_mask ? (mask && grad_mask) : (grad_dists != nullptr), ACFM_ERR_BAD_ARG, "%s: null gradient pointer", who);
+  ACFM_REQUIRE(from_mask ? (mask && (grad_mask || grad_sums)) : (grad_dists != nullptr), ACFM_ERR_BAD_ARG, "%s: null gradient pointer", who);
+  ACFM_REQUIRE(!grad_sums || (loss_target && NB > 0 && N % NB == 0), ACFM_ERR_BAD_ARG, "%s: fused losses need the target and N %% NB == 0", who);
   ACFM_REQUIRE(F <= 65535 && V <= 65535, ACFM_ERR_UNSUPPORTED, "%s: V=%d, F=%d must be <= 65535", who, V, F);
   cudaStream_t st = (cudaStream_t)stream;
   ACFM_CUDA_OK(cudaMemsetAsync(grad_ndc, 0, sizeof(float) * 3 * (size_t)N * V, st));
@@ -299,6 +324,7 @@ int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* fa
   p.N = N; p.V = V; p.F = F; p.H = H; p.W = W; p.K = K; p.sigma = from_mask ? sigma : 1.0f;
   p.p2f = (const long long*)pix_to_face; p.dists = dists; p.mask = mask; p.grad_mask = grad_mask; p.grad_dists = grad_dists;
   p.grad_ndc = grad_ndc;
+  p.grad_sums = grad_sums; p.loss_target = loss_target; p.loss_edt = loss_edt; p.NB = NB > 0 ? NB : 1;
   p.work = (const int*)work;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
   const BwdSmem L(V, F);
@@ -325,6 +351,14 @@ extern "C" int acfm_raster_soft_bwd(const float* ndc, const void* faces, int fac
                                     const void* fwd_workspace, void* stream) {
   return launch_bwd("acfm_raster_soft_bwd", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma,
                     pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, fwd_workspace, stream);
+}
+
+extern "C" int acfm_raster_soft_bwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                                           int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
+                                           const float* mask, const float* grad_mask, const float* grad_sums, const float* target,
+                                           const float* edt, int NB, float* grad_ndc, const void* fwd_workspace, void* stream) {
+  return launch_bwd("acfm_raster_soft_bwd_losses", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma,
+                    pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, fwd_workspace, stream, grad_sums, target, edt, NB);
 }
 
 extern "C" int acfm_raster_dists_bwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,

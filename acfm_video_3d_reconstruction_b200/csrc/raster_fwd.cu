@@ -78,6 +78,11 @@ struct RasterParams {
   int vec_ok;   // output pointers are 16-byte aligned
   int bulk_ok;  // rows of the fragment tensors are 16-byte aligned: the padding kernel may use bulk stores
   int pad_balance;  // bytes of padding per live region above which every padding CTA works (else 5/8 of them)
+  // fused silhouette losses (optional): targets read at render n % NB, per-(render, region) partial sums out
+  const float* loss_target;  // (NB,H,W) or NULL
+  const float* loss_edt;     // (NB,H,W) or NULL
+  int NB;
+  float* loss_part;          // (N * regions, 4), zeroed by the host entry
   const int* work;  // split path, written by raster_prep_kernel: {live, fill runs, empty regions, -, live per weight class [4],
                     //   listR[4][N*regions], listF[N*regions][2]}
 };
@@ -87,7 +92,7 @@ __host__ __device__ inline int fill_pattern_slots(int K) { return max(kRegion * 
 
 // shared-memory carve-up, identical on host and device
 struct FwdSmem {
-  int off_ndc, off_red, off_hist, off_tw, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
+  int off_ndc, off_red, off_hist, off_tw, off_ts, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
   int w_z, w_d, w_f, w_o, w_q, w_cnt, w_ord;  // offsets inside one warp's slab
   int KS;                                     // per-lane row stride in entries
   __host__ __device__ FwdSmem(int V, int F, int K, int nwarps, int cap) {
@@ -96,6 +101,7 @@ struct FwdSmem {
     off_red = o; o += nwarps * 32;
     off_hist = o; o += kZBuckets * 4;
     off_tw = o; o += 32 * 4;  // faces per 8x4 tile of the region (tile order: heaviest first)
+    off_ts = o; o += 32 * 4 * 4;  // fused losses: four partial sums per tile (one slot per tile: order-independent)
     off_rlist = o; o += ((F * 2 + 15) / 16) * 16;  // ushort per region face
     off_recA = o; o += cap * 64;                   // 4 float4 arrays (scan / filter data)
     off_recB = o; o += cap * 64;                   // 4 float4 arrays (exact evaluation data)
@@ -520,6 +526,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
   float* red = reinterpret_cast<float*>(smem + L.off_red);
   int* hist = reinterpret_cast<int*>(smem + L.off_hist);
   int* tw = reinterpret_cast<int*>(smem + L.off_tw);
+  float* tsum = reinterpret_cast<float*>(smem + L.off_ts);  // [32 tiles][4]
   unsigned short* rlist = reinterpret_cast<unsigned short*>(smem + L.off_rlist);
   float4* recA = reinterpret_cast<float4*>(smem + L.off_recA);  // [4][cap]: bbox | g0 g1.x | g1.yz g2.xy | g2.z
   float4* recB = reinterpret_cast<float4*>(smem + L.off_recB);  // [4][cap]: x0 y0 x1 y1 | x2 y2 z0 z1 | z2 den yden flags | r01 r02 r12
@@ -562,6 +569,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
     }
     if (tid < kZBuckets) hist[tid] = 0;
     if (tid < 32) tw[tid] = 0;
+    if (tid < 128) tsum[tid] = 0.0f;
     raster_sync<NT>();
 #pragma unroll
     for (int w = 0; w < NWARPS; ++w) {
@@ -860,6 +868,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         vo[(int)fp[0]] = 1.0f; vo[(int)fp[1]] = 1.0f; vo[(int)fp[2]] = 1.0f;
       }
     }
+    float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
     if (p.mask && valid) {
       float alpha = 1.0f;
       for (int i = 0; i < cnt; ++i) {  // in depth order, like the reference's product (the bits of the mask do not depend on
@@ -868,6 +877,24 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         alpha *= __fdividef(1.0f, 1.0f + __expf(-ks.d[ord[i]] * inv_sigma_neg));
       }
       p.mask[((long long)n * p.H + yi) * p.W + xi] = 1.0f - alpha;
+      if (p.loss_part) {
+        // fused silhouette losses (l1 / iou / edt, loss_utils.py:18-32,72-77,245-253): this pixel's share of
+        // sum(|m-t| - |t|), sum m t, sum (m - m t), sum edt m — the parts that vanish where the mask is 0, so that regions and
+        // tiles without fragments contribute nothing and the sums over the bare target are added once per render afterwards
+        const float m = 1.0f - alpha;
+        const size_t ti = ((size_t)(n % p.NB) * p.H + yi) * p.W + xi;
+        const float t = p.loss_target[ti];
+        l0 = fabsf(m - t) - fabsf(t); l1 = m * t; l2 = m - m * t;
+        l3 = p.loss_edt ? p.loss_edt[ti] * m : 0.0f;
+      }
+    }
+    if (p.loss_part) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, o); l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        l2 += __shfl_xor_sync(0xffffffffu, l2, o); l3 += __shfl_xor_sync(0xffffffffu, l3, o);
+      }
+      if (lane == 0) { tsum[tbit * 4] = l0; tsum[tbit * 4 + 1] = l1; tsum[tbit * 4 + 2] = l2; tsum[tbit * 4 + 3] = l3; }
     }
     cnts[lane] = (unsigned char)cnt;
     __syncwarp();
@@ -959,6 +986,16 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
       }
     }
     __syncwarp();  // the lists are reused by the next tile
+  }
+  if (p.loss_part) {
+    // the region's four partial sums: the 32 tile slots added in tile order (not in the order the warps happened to pull them)
+    raster_sync<NT>();
+    if (tid < 4) {
+      float a = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) a += tsum[t * 4 + tid];
+      p.loss_part[(size_t)unit * 4 + tid] = a;
+    }
   }
 }
 
@@ -1281,7 +1318,54 @@ int fwd_config(int V, int F, int K, int* smem, int* cap) {
   return nw;
 }
 
+// ---- fused silhouette losses: the reductions around the rasterizer ---------------------------------------------------------
+// base[b] = { sum |t_b|, sum t_b } over the bare target b (what the four sums are where the mask is 0); one CTA per target
+__global__ void __launch_bounds__(256) loss_target_base_kernel(const float* __restrict__ target, int HW, float* __restrict__ base) {
+  const float* t = target + (size_t)blockIdx.x * HW;
+  float a = 0.0f, b = 0.0f;
+  for (int i = threadIdx.x; i < HW; i += 256) { const float v = t[i]; a += fabsf(v); b += v; }
+  __shared__ float red[8][2];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = a; red[threadIdx.x >> 5][1] = b; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    base[blockIdx.x * 2 + threadIdx.x] = s;
+  }
+}
+
+// sums[n] = { sum|m-t|, sum m t, sum (m+t-mt), sum edt m } = the render's region partials (fixed order) + the target's base
+__global__ void __launch_bounds__(32) loss_reduce_kernel(const float* __restrict__ part, const float* __restrict__ base, int regions,
+                                                         int NB, float* __restrict__ sums) {
+  const int n = blockIdx.x, lane = threadIdx.x;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  for (int r = lane; r < regions; r += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)n * regions + r) * 4);
+    a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if (lane == 0) {
+    const float* b = base + (size_t)(n % NB) * 2;
+    *reinterpret_cast<float4*>(sums + (size_t)n * 4) = make_float4(a0 + b[0], a1, a2 + b[1], a3);
+  }
+}
+
 }  // namespace
+
+namespace {
+int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F, int H,
+                    int W, int K, float blur_radius, int clip_bary, int cull_backfaces, float sigma, int64_t* pix_to_face,
+                    float* zbuf, float* dists, float* bary, float* mask, float* visible_verts, const float* loss_target,
+                    const float* loss_edt, int NB, float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+}
 
 extern "C" int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes, int* num_ctas,
                                            int* threads) {
@@ -1299,6 +1383,34 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
                                int V, int F, int H, int W, int K, float blur_radius, int clip_bary, int cull_backfaces,
                                float sigma, int64_t* pix_to_face, float* zbuf, float* dists, float* bary, float* mask,
                                float* visible_verts, void* workspace, int64_t workspace_bytes, void* stream) {
+  return raster_fwd_impl(ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, blur_radius, clip_bary, cull_backfaces, sigma,
+                         pix_to_face, zbuf, dists, bary, mask, visible_verts, nullptr, nullptr, 0, nullptr, nullptr, 0, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int64_t acfm_raster_loss_workspace_bytes(int N, int NB, int H, int W) {
+  if (N <= 0 || NB <= 0 || H <= 0 || W <= 0) return 0;
+  return 16 * (int64_t)N * ((W + kRegion - 1) / kRegion) * ((H + kRegion - 1) / kRegion) + 8 * (int64_t)NB;
+}
+
+extern "C" int acfm_raster_fwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                                      int F, int H, int W, int K, float blur_radius, float sigma, int64_t* pix_to_face, float* zbuf,
+                                      float* dists, float* mask, float* visible_verts, const float* target, const float* edt, int NB,
+                                      float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
+  ACFM_REQUIRE(target && loss_sums && loss_workspace && mask, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_losses: null pointer");
+  ACFM_REQUIRE(NB > 0 && N % NB == 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_losses: N=%d is not a multiple of NB=%d", N, NB);
+  return raster_fwd_impl(ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, blur_radius, 0, 0, sigma, pix_to_face, zbuf,
+                         dists, nullptr, mask, visible_verts, target, edt, NB, loss_sums, loss_workspace, loss_workspace_bytes,
+                         workspace, workspace_bytes, stream);
+}
+
+namespace {
+int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F, int H,
+                    int W, int K, float blur_radius, int clip_bary, int cull_backfaces, float sigma, int64_t* pix_to_face,
+                    float* zbuf, float* dists, float* bary, float* mask, float* visible_verts, const float* loss_target,
+                    const float* loss_edt, int NB, float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes,
+                    void* workspace, int64_t workspace_bytes, void* stream) {
   ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: bad sizes N=%d V=%d F=%d H=%d W=%d", N, V, F, H, W);
   ACFM_REQUIRE(K >= 1, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: faces_per_pixel K=%d must be >= 1", K);
   ACFM_REQUIRE(K <= 64, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: faces_per_pixel K=%d > 64 is not supported", K);
@@ -1315,6 +1427,7 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   p.blur = blur_radius; p.sq_blur = sqrtf(blur_radius); p.sigma = sigma;
   p.clip = clip_bary; p.cull = cull_backfaces;
   p.k_eps = acfm_raster_epsilon();
+  p.loss_target = loss_target; p.loss_edt = loss_edt; p.NB = NB > 0 ? NB : 1; p.loss_part = nullptr;
   p.p2f = (long long*)pix_to_face; p.zbuf = zbuf; p.dists = dists; p.bary = bary; p.mask = mask; p.vis = visible_verts;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
   p.vec_ok = ((((uintptr_t)pix_to_face) | ((uintptr_t)zbuf) | ((uintptr_t)dists)) & 15u) == 0;
@@ -1327,6 +1440,15 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   ACFM_REQUIRE(ctas < (1ll << 28), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: too many CTAs");
   cudaStream_t st = (cudaStream_t)stream;
   if (visible_verts && V > 0) ACFM_CUDA_OK(cudaMemsetAsync(visible_verts, 0, sizeof(float) * (size_t)N * V, st));
+  if (loss_sums) {
+    // fused losses: region partials (zero where nothing is rendered) + per-target base sums, both in the caller's scratch
+    ACFM_REQUIRE(loss_workspace_bytes >= 16 * ctas + 8 * (long long)NB && (((uintptr_t)loss_workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
+                 "acfm_raster_fwd_losses: loss workspace must be 16-byte aligned and hold acfm_raster_loss_workspace_bytes()");
+    p.loss_part = (float*)loss_workspace;
+    ACFM_CUDA_OK(cudaMemsetAsync(p.loss_part, 0, 16 * (size_t)ctas, st));
+    loss_target_base_kernel<<<NB, 256, 0, st>>>(loss_target, H * W, p.loss_part + 4 * ctas);
+    ACFM_LAUNCH_OK("loss_target_base_kernel");
+  }
   // split path (see raster_prep_kernel): needs the caller's scratch; without it the rasterizer kernel pads the empty regions
   const FwdTuning& tune = fwd_tuning();
   p.bulk_ok = 0; p.pad_balance = tune.pad_balance;
@@ -1364,8 +1486,13 @@ extern "C" int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i6
   else if (nw == 4) ACFM_FWD_CASE(4, 0);
 #undef ACFM_FWD_CASE
   ACFM_REQUIRE(rc != ACFM_ERR_UNSUPPORTED, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: no launch configuration");
+  if (rc == ACFM_OK && loss_sums) {
+    loss_reduce_kernel<<<N, 32, 0, st>>>(p.loss_part, p.loss_part + 4 * ctas, p.regions_x * p.regions_y, NB, loss_sums);
+    ACFM_LAUNCH_OK("loss_reduce_kernel");
+  }
   return rc;
 }
+}  // namespace
 
 extern "C" int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W) {
   if (N <= 0 || H <= 0 || W <= 0) return 0;

@@ -75,7 +75,7 @@ class HandleSolver:
     per-step part, lbs lbs^T, has rank K_h.  With P~ = L^T L + (c/V) 1 1^T (full rank; inverted ONCE, here, in fp64) and
     U~ = [lbs, 1], S = diag(I, -c/V):   M = P~ + U~ S U~^T  and Woodbury gives  W = (P~^-1 U~) C^-1 [:, :K_h],
     C = S^-1 + U~^T P~^-1 U~.  The per-step part runs in libacfm_b200 (csrc/handle_solve.cu: acfm_handle_solve_fwd / _bwd,
-    fp64, 3 + 5 kernels, deterministic) instead of a V x V Cholesky factorisation and two V x V triangular solves per FRAME in
+    fp64, 4 + 7 small kernels, deterministic) instead of a V x V Cholesky factorisation and two V x V triangular solves per FRAME in
     the reference.  fp64 keeps the result at the accuracy of the direct fp64 solve (cond(P~) ~ 1e4-1e5); W is returned in
     fp32.  Differentiable w.r.t. lbs (closed-form backward)."""
 
@@ -91,6 +91,7 @@ class HandleSolver:
         null_resid = float(Ld.matmul(ones).abs().max())
         try:
             self.Pinv = torch.linalg.inv(Pt).contiguous()
+            self.Pinv_ones = self.Pinv.sum(1).contiguous()          # Pinv 1: the constant last column of Pinv [lbs, 1]
             resid = float((self.Pinv.matmul(Pt) - torch.eye(V, dtype=torch.float64, device=L.device)).abs().max())
             self.ok = bool(torch.isfinite(self.Pinv).all()) and resid < 1e-6 and null_resid < 1e-5 and self.c > 0 and L.is_cuda
         except RuntimeError:
@@ -115,10 +116,10 @@ class _SolverMatrix(torch.autograd.Function):
         ws = solver.workspace(Kh)
         W = torch.empty((V, Kh), dtype=torch.float32, device=lbs.device)
         with torch.cuda.device(lbs.device):
-            st = _lib.lib().acfm_handle_solve_fwd(_lib.ptr(solver.Pinv), _lib.ptr(lbs), V, Kh, solver.c / V, _lib.ptr(W),
-                                                  _lib.ptr(ws), ws.numel(), _lib.stream_of(lbs))
+            st = _lib.lib().acfm_handle_solve_fwd(_lib.ptr(solver.Pinv), _lib.ptr(solver.Pinv_ones), _lib.ptr(lbs), V, Kh, solver.c / V,
+                                                  _lib.ptr(W), _lib.ptr(ws), ws.numel(), _lib.stream_of(lbs))
         _lib.check(st, "acfm_handle_solve_fwd")
-        _lib.count(3)
+        _lib.count(4)
         ctx.solver, ctx.ws = solver, ws
         ctx.save_for_backward(lbs)
         return W
@@ -133,7 +134,7 @@ class _SolverMatrix(torch.autograd.Function):
             st = _lib.lib().acfm_handle_solve_bwd(_lib.ptr(ctx.solver.Pinv), _lib.ptr(lbs), _lib.ptr(gW), V, Kh, _lib.ptr(g),
                                                   _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_of(lbs))
         _lib.check(st, "acfm_handle_solve_bwd")
-        _lib.count(5)
+        _lib.count(7)
         return g, None
 
 

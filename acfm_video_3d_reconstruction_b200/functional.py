@@ -130,8 +130,6 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
                                         _lib.ptr(mask), _lib.ptr(vis), _lib.ptr(ws), ws_bytes, _lib.stream_of(ndc))
     _lib.check(st, "acfm_raster_fwd")
     _lib.count((2 if ws is not None else 1) + (1 if vis is not None else 0))
-    if vis is not None:
-        p2f._acfm_vis = vis   # picked up by loss_utils.visible_vertices
     if _lib.event_hook is not None:
         _lib.event_hook("raster_fwd", 1)
     return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask, vis=vis, work=ws)
@@ -177,10 +175,92 @@ class _SoftSilhouette(torch.autograd.Function):
 
 
 def soft_silhouette(ndc, faces, image_size, blur_radius=BLUR_SOFT, faces_per_pixel=K_SOFT, sigma=SIGMA, want_vis=False):
-    """-> mask, pix_to_face, zbuf, dists.  want_vis: the render also marks the visible vertices; the (N,V) map rides on the
-    returned pix_to_face tensor (attribute `_acfm_vis`), where loss_utils.bds_loss finds it."""
-    out = _SoftSilhouette.apply(ndc, faces, int(image_size), float(blur_radius), int(faces_per_pixel), float(sigma), bool(want_vis))
-    if want_vis:
-        out[1]._acfm_vis = out[4]
-        return out[:4]
-    return out
+    """-> mask, pix_to_face, zbuf, dists [, vis].  want_vis: the render also marks the visible vertices — (N,V) 0/1 floats,
+    what bds_loss / optical_flow_loss derive from pix_to_face[..., 0] — returned as a fifth tensor (pass it to the losses as
+    `visible=`)."""
+    return _SoftSilhouette.apply(ndc, faces, int(image_size), float(blur_radius), int(faces_per_pixel), float(sigma), bool(want_vis))
+
+
+class _SoftSilhouetteLosses(torch.autograd.Function):
+    """The soft-silhouette render with the per-render mask-loss sums fused in (acfm_raster_fwd_losses / _soft_bwd_losses):
+    ndc (N,V,3), target (NB,H,W), edt (NB,H,W) or None -> mask, pix_to_face, zbuf, dists, sums (N,4) [, vis].
+    Differentiable in ndc through BOTH the mask and the sums; d loss / d mask of the sums is formed inside the rasterizer
+    backward and never materialised."""
+
+    @staticmethod
+    def forward(ctx, ndc, faces, target, edt, image_size, blur_radius, K, sigma, want_vis):
+        _lib.require_cuda(ndc, faces, target, edt)
+        ndc, target = _f32c(ndc), _f32c(target)
+        edt = _f32c(edt) if edt is not None else None
+        N, V, _ = ndc.shape
+        H = W = int(image_size)
+        NB = target.shape[0]
+        if N and (NB == 0 or N % NB or target.numel() != NB * H * W or (edt is not None and edt.numel() != target.numel())):
+            raise ValueError(f"renders {N} vs target {tuple(target.shape)}: the batch must divide, the pixels must match")
+        fa, i64, fstride, F = _faces_arg(faces, N)
+        dev = ndc.device
+        p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        mask = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+        sums = torch.empty((N, 4), dtype=torch.float32, device=dev)
+        vis = torch.empty((N, V), dtype=torch.float32, device=dev) if want_vis else None
+        L = _lib.lib()
+        ws_bytes = int(L.acfm_raster_fwd_workspace_bytes(N, H, W))
+        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+        lw_bytes = int(L.acfm_raster_loss_workspace_bytes(N, max(NB, 1), H, W))
+        lw = torch.empty((max(lw_bytes, 16),), dtype=torch.uint8, device=dev)
+        if _lib.event_hook is not None:
+            _lib.event_hook("raster_fwd", 0)
+        if N:
+            with torch.cuda.device(dev):
+                st = L.acfm_raster_fwd_losses(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K, float(blur_radius),
+                                              float(sigma), _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), _lib.ptr(mask),
+                                              _lib.ptr(vis), _lib.ptr(target), _lib.ptr(edt), NB, _lib.ptr(sums), _lib.ptr(lw),
+                                              lw_bytes, _lib.ptr(ws), ws_bytes, _lib.stream_of(ndc))
+            _lib.check(st, "acfm_raster_fwd_losses")
+            _lib.count(5 + (1 if vis is not None else 0))  # prep, padding, rasterizer, target base, reduce
+        if _lib.event_hook is not None:
+            _lib.event_hook("raster_fwd", 1)
+        ctx.save_for_backward(ndc, faces, p2f, dists, mask, target, edt)
+        ctx.cfg = (H, int(K), float(sigma))
+        ctx.work = ws
+        ctx.mark_non_differentiable(p2f, zbuf, dists)
+        ctx.set_materialize_grads(False)
+        if want_vis:
+            ctx.mark_non_differentiable(vis)
+            return mask, p2f, zbuf, dists, sums, vis
+        return mask, p2f, zbuf, dists, sums
+
+    @staticmethod
+    def backward(ctx, grad_mask, _g1, _g2, _g3, grad_sums, _g5=None):
+        ndc, faces, p2f, dists, mask, target, edt = ctx.saved_tensors
+        S, K, sigma = ctx.cfg
+        N, V, _ = ndc.shape
+        none = (None,) * 9
+        if (grad_mask is None and grad_sums is None) or N == 0:
+            return none
+        fa, i64, fstride, F = _faces_arg(faces, N)
+        grad_mask = _f32c(grad_mask) if grad_mask is not None else None
+        grad_sums = _f32c(grad_sums) if grad_sums is not None else None
+        g = torch.empty_like(ndc)
+        if _lib.event_hook is not None:
+            _lib.event_hook("raster_bwd", 0)
+        with torch.cuda.device(ndc.device):
+            st = _lib.lib().acfm_raster_soft_bwd_losses(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma,
+                                                        _lib.ptr(p2f), _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(grad_mask),
+                                                        _lib.ptr(grad_sums), _lib.ptr(target), _lib.ptr(edt), target.shape[0],
+                                                        _lib.ptr(g), _lib.ptr(ctx.work), _lib.stream_of(ndc))
+        _lib.check(st, "acfm_raster_soft_bwd_losses")
+        _lib.count(2)  # memset + kernel
+        if _lib.event_hook is not None:
+            _lib.event_hook("raster_bwd", 1)
+        return (g,) + none[1:]
+
+
+def soft_silhouette_losses(ndc, faces, image_size, target, edt=None, blur_radius=BLUR_SOFT, faces_per_pixel=K_SOFT, sigma=SIGMA,
+                           want_vis=False):
+    """-> mask, pix_to_face, zbuf, dists, sums (N,4) [, vis]; sums = {sum|m-t|, sum m t, sum (m+t-mt), sum edt m} per render
+    (loss_utils.losses_from_sums turns them into l1 / iou / edt losses)."""
+    return _SoftSilhouetteLosses.apply(ndc, faces, target, edt, int(image_size), float(blur_radius), int(faces_per_pixel),
+                                       float(sigma), bool(want_vis))

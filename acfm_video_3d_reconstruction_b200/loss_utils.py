@@ -49,14 +49,19 @@ def mask_sums(mask, target, edt=None):
     return _MaskSums.apply(mask, target, edt)
 
 
-def mask_losses(mask, target, edt=None):
-    """All per-render silhouette losses in one pass: dict(l1, iou_loss, edt) each (N,)."""
-    s = mask_sums(mask, target, edt)
-    hw = float(mask[0].numel()) if mask.shape[0] else 1.0
+def losses_from_sums(s, pixels, with_edt=True):
+    """(N,4) sums of mask_sums() or of NeuralRenderer.forward_with_losses -> dict(l1, iou_loss[, edt]) each (N,):
+    l1_loss / iou_loss / edt_loss with reduce=False (loss_utils.py:18-32,72-77,245-253)."""
+    hw = float(pixels)
     out = dict(l1=s[:, 0] / hw, iou_loss=1 - s[:, 1] / (s[:, 2] + 1e-6))
-    if edt is not None:
+    if with_edt:
         out["edt"] = s[:, 3] / hw
     return out
+
+
+def mask_losses(mask, target, edt=None):
+    """All per-render silhouette losses in one pass over a rendered mask: dict(l1, iou_loss, edt) each (N,)."""
+    return losses_from_sums(mask_sums(mask, target, edt), mask[0].numel() if mask.shape[0] else 1, edt is not None)
 
 
 def _reduce(per_render, reduce):
@@ -127,9 +132,6 @@ def visible_vertices(pix_to_face, faces, num_verts):
     """(N,V) 0/1 floats: vertices of the faces that are nearest at some pixel — the fi_maps/unique/scatter_ block of
     bds_loss (loss_utils.py:213-223) and optical_flow_loss (:432-441).  pix_to_face (N,H,W,K) int64 packed ids."""
     _lib.require_cuda(pix_to_face, faces)
-    fused = getattr(pix_to_face, "_acfm_vis", None)   # written by the render itself (functional.rasterize(want_vis=True))
-    if fused is not None and fused.shape == (pix_to_face.shape[0], num_verts):
-        return fused
     if pix_to_face.dtype != torch.int64:
         pix_to_face = pix_to_face.long()
     pix_to_face = pix_to_face.contiguous()
@@ -176,26 +178,30 @@ class _BdsLoss(torch.autograd.Function):
         return gv, None, None, None
 
 
-def bds_loss(verts, bds, faces, pix_to_face, reduce=True, n_samples=1000, k=1, indices=None):
+def bds_loss(verts, bds, faces, pix_to_face, reduce=True, n_samples=1000, k=1, indices=None, visible=None):
     """loss_utils.py:204-237.  verts (N,V,2|3) projected vertices, bds (NB|N,P,3) boundary points [x,y,mask],
     faces (N,F,3), pix_to_face (N,H,W,K).  Like the reference, up to n_samples boundary points are drawn with
     torch.randperm from the default (CPU) generator on every call — unless `indices` (int64, on the device) is given,
-    which keeps the call free of host work (CUDA-graph capture, predictor.PostOptimizer)."""
+    which keeps the call free of host work (CUDA-graph capture, predictor.PostOptimizer).
+    visible (N,V): the visible-vertex map when the render already produced it (NeuralRenderer.forward_with_visibility /
+    forward_with_losses); otherwise it is derived from pix_to_face[..., 0] as the reference does (same values)."""
     if k != 1:
         raise ValueError("bds_loss: only k=1 (the reference's only call) is implemented")
     _lib.require_cuda(verts, bds, faces, pix_to_face)
     if indices is None:
         indices = torch.randperm(bds.shape[1])[:n_samples].to(verts.device)
-    vis = visible_vertices(pix_to_face, faces, verts.shape[1])
-    loss = _BdsLoss.apply(verts, vis, bds, indices.contiguous())
+    vis = visible if visible is not None else visible_vertices(pix_to_face, faces, verts.shape[1])
+    if vis.shape != (verts.shape[0], verts.shape[1]):
+        raise ValueError(f"visible must be (N,V) = {(verts.shape[0], verts.shape[1])}, got {tuple(vis.shape)}")
+    loss = _BdsLoss.apply(verts, F_._f32c(vis), bds, indices.contiguous())
     return loss.mean() if reduce else loss
 
 
 class Boundaries_Loss(torch.nn.Module):
     """loss_utils.py:240-242"""
 
-    def forward(self, verts, bds, faces, pix_to_face, reduce=True, n_samples=1000):
-        return bds_loss(verts, bds, faces, pix_to_face, reduce=reduce, n_samples=n_samples)
+    def forward(self, verts, bds, faces, pix_to_face, reduce=True, n_samples=1000, visible=None):
+        return bds_loss(verts, bds, faces, pix_to_face, reduce=reduce, n_samples=n_samples, visible=visible)
 
 
 class _OfLoss(torch.autograd.Function):
@@ -239,22 +245,25 @@ class _OfLoss(torch.autograd.Function):
         return gp, None, None, None, None
 
 
-def optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=True):
+def optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=True, visible=None):
     """loss_utils.py:419-474.  meshes (B,T,V,3), faces (B,T,F,3), cams (B*T,7), flows (B|B/G,T,H,W,2);
     renderer: an OF_NeuralRenderer (its proj_fn projects, its forward gives the K=1 visibility render when
-    pix_to_face is None).  Returns (loss, of_pred, visible_vertices, predicted_points, samples_ofs_gt) as the
-    reference does."""
+    pix_to_face is None).  visible (B*T,V): the visible-vertex map, if a render already produced it.
+    Returns (loss, of_pred, visible_vertices, predicted_points, samples_ofs_gt) as the reference does."""
     _lib.require_cuda(meshes, faces, cams, flows)
     b, t, nv, _ = meshes.shape
     bt = b * t
     predicted_points = renderer.proj_fn(meshes.reshape(bt, nv, -1), cams.reshape(bt, -1))
     faces_bt = faces.reshape(bt, faces.shape[2], 3)
     with torch.no_grad():
-        if pix_to_face is None:
-            pix_to_face = renderer(predicted_points.reshape(bt, nv, 3), faces_bt)
-        elif getattr(pix_to_face, "_acfm_vis", None) is None:
-            pix_to_face = pix_to_face[..., :1]
-        vis = visible_vertices(pix_to_face, faces_bt, nv)
+        if visible is not None:
+            vis = F_._f32c(visible).reshape(bt, nv)
+        elif pix_to_face is None and hasattr(renderer, "forward_with_visibility"):
+            _, vis = renderer.forward_with_visibility(predicted_points.reshape(bt, nv, 3), faces_bt)   # the K = 1 render marks them itself
+        else:
+            if pix_to_face is None:
+                pix_to_face = renderer(predicted_points.reshape(bt, nv, 3), faces_bt)
+            vis = visible_vertices(pix_to_face[..., :1], faces_bt, nv)
     flows_bt = flows.reshape(-1, flows.shape[2], flows.shape[3], flows.shape[4])
     loss, of_pred, vis_out, samples = _OfLoss.apply(predicted_points, vis, flows_bt, b, t)
     if reduce:
@@ -265,8 +274,8 @@ def optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=
 class Optical_Flow_Loss(torch.nn.Module):
     """loss_utils.py:477-479"""
 
-    def forward(self, meshes, faces, cams, flows, renderer, pix_to_face, reduce=True):
-        return optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=reduce)
+    def forward(self, meshes, faces, cams, flows, renderer, pix_to_face, reduce=True, visible=None):
+        return optical_flow_loss(meshes, faces, cams, flows, renderer, pix_to_face, reduce=reduce, visible=visible)
 
 
 class _HypWeight(torch.autograd.Function):

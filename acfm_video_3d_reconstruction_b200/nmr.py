@@ -6,10 +6,15 @@ signatures; the PyTorch3D 0.3.0 objects they used to build per call are replaced
 kernels of libacfm_b200.so (projection -> tile-binned rasterizer -> fused blend, and their backward).
 Modules hold no parameters or buffers and are re-entrant (DataParallel replicas, main.py:184-193).
 """
+import collections
+
 import torch
 
 from . import functional as F_
 from . import geom_utils
+
+# what PyTorch3D's MeshRasterizer returns (pytorch3d.renderer.mesh.rasterizer.Fragments): rasterize_of() hands it back
+Fragments = collections.namedtuple("Fragments", ["pix_to_face", "zbuf", "bary_coords", "dists"])
 
 
 class NeuralRenderer(torch.nn.Module):
@@ -17,7 +22,13 @@ class NeuralRenderer(torch.nn.Module):
          -> (masks[N,H,W], pix_to_face[N,H,W,20])                      if textures is None
          -> (imgs[N,3,H,W], sil[N,H,W], pix_to_face[N,H,W,1])          otherwise
     offset_z: 0.0 is the multiframe default (multiframe/nnutils/nmr.py:119); the monocular tree
-    uses 5.0 (monocular/nnutils/nmr.py:164) — pass offset_z=5. or set the attribute."""
+    uses 5.0 (monocular/nnutils/nmr.py:164): `acfm_video_3d_reconstruction_b200.monocular.NeuralRenderer` has that
+    default, `...multiframe.NeuralRenderer` this one, so that each tree's `from nnutils.nmr import NeuralRenderer`
+    can be pointed at its own module without touching a call site.
+
+    Beyond the reference's interface (opt-in, same kernels): forward_with_visibility() also returns the visible-vertex map
+    that bds_loss / optical_flow_loss need, forward_with_losses() also returns the per-render mask-loss sums fused into the
+    render.  K = faces_per_pixel <= 64 (PyTorch3D allows 150; the reference uses 20 and 1)."""
 
     def __init__(self, img_size=256, offset_z=0.):
         super(NeuralRenderer, self).__init__()
@@ -29,9 +40,6 @@ class NeuralRenderer(torch.nn.Module):
         self.sigma = F_.SIGMA
         self.blur_radius = F_.BLUR_SOFT
         self.faces_per_pixel = F_.K_SOFT
-        # True: the mask render also marks the visible vertices (rides on the returned pix_to_face; bds_loss uses it
-        # instead of re-reading pix_to_face[..., 0]).  Set it where the boundary loss follows the render (multiframe).
-        self.emit_visibility = False
 
     def ambient_light_only(self):
         return
@@ -47,12 +55,40 @@ class NeuralRenderer(torch.nn.Module):
         """proj_fn + `vs[:, :, 1] *= -1` + R=diag(-1,1,1), T=(0,0,2.732) (nmr.py:144-149)."""
         return F_.project(vertices, cams, offset_z=self.offset_z, sx=-1.0, sy=-1.0, z_add=F_.EYE_Z)
 
+    def rasterize_of(self, verts, faces, R, T):
+        """nmr.py:131-141 (defined by the reference, called by none of its paths): hard K = 1 rasterization of `verts` under
+        the view X R + T (PyTorch3D's row-vector convention, identity SfM-orthographic projection) -> Fragments."""
+        with torch.no_grad():
+            view = torch.matmul(verts, R.to(verts.dtype)) + T.to(verts.dtype)[:, None, :]
+            fr = F_.rasterize(view, faces, self.img_size, 0.0, 1, want_bary=True)
+        return Fragments(fr["pix_to_face"], fr["zbuf"], fr["bary"], fr["dists"])
+
+    def forward_with_visibility(self, vertices, faces, cams):
+        """-> (masks, pix_to_face, visible[N,V]): the mask render that also marks the vertices of every pixel's nearest face —
+        pass `visible=` to loss_utils.bds_loss / optical_flow_loss, which otherwise re-read pix_to_face[..., 0]."""
+        self.mask_only = True
+        masks, pix_to_face, _, _, vis = F_.soft_silhouette(self.to_ndc(vertices, cams), faces, self.img_size, self.blur_radius,
+                                                           self.faces_per_pixel, self.sigma, want_vis=True)
+        return masks, pix_to_face, vis
+
+    def forward_with_losses(self, vertices, faces, cams, mask_gt, edt=None, want_visibility=False):
+        """-> (masks, pix_to_face, sums[N,4][, visible]).  sums = {sum|m-t|, sum m t, sum (m+t-mt), sum edt m} per render,
+        accumulated in the render's epilogue (loss_utils.losses_from_sums -> l1 / iou / edt losses); their backward runs
+        inside the rasterizer backward, so neither a second pass over the mask nor grad_mask exists.  mask_gt / edt
+        (NB,H,W) with NB | N: render n uses entry n % NB (the callers' .repeat(num_guesses, 1, 1), main.py:644,716)."""
+        self.mask_only = True
+        out = F_.soft_silhouette_losses(self.to_ndc(vertices, cams), faces, self.img_size,
+                                        mask_gt.reshape(mask_gt.shape[0], self.img_size, self.img_size),
+                                        None if edt is None else edt.reshape(edt.shape[0], self.img_size, self.img_size),
+                                        self.blur_radius, self.faces_per_pixel, self.sigma, want_vis=want_visibility)
+        return (out[0], out[1], out[4]) + ((out[5],) if want_visibility else ())
+
     def forward(self, vertices, faces, cams, textures=None, atlas=True):
         ndc = self.to_ndc(vertices, cams)
         if textures is None:
             self.mask_only = True
             masks, pix_to_face, _, _ = F_.soft_silhouette(ndc, faces, self.img_size, self.blur_radius,
-                                                          self.faces_per_pixel, self.sigma, want_vis=self.emit_visibility)
+                                                          self.faces_per_pixel, self.sigma)
             return masks, pix_to_face
         self.mask_only = False
         from . import texture
@@ -73,10 +109,18 @@ class OF_NeuralRenderer(torch.nn.Module):
         proj = self.proj_fn(verts, cams)
         return proj[:, :, :2]
 
-    def forward(self, verts, faces):
+    def _render(self, verts, faces, want_vis):
         with torch.no_grad():
             # R = diag(-1,1,1), T = (0,0,2.732): exact sign flip, one rounding on z
             # no host-side constants here (keeps the call CUDA-graph capturable)
             ndc = torch.stack([-verts[..., 0], verts[..., 1], verts[..., 2] + F_.EYE_Z], dim=-1)
-            fr = F_.rasterize(ndc, faces, self.img_size, 0.0, 1, want_vis=True)   # its only consumer needs the visibility
-        return fr["pix_to_face"]
+            return F_.rasterize(ndc, faces, self.img_size, 0.0, 1, want_vis=want_vis)
+
+    def forward(self, verts, faces):
+        return self._render(verts, faces, False)["pix_to_face"]
+
+    def forward_with_visibility(self, verts, faces):
+        """-> (pix_to_face, visible[N,V]): the render's only consumer, optical_flow_loss, needs the visible vertices; the
+        render marks them itself instead of leaving a strided re-read of pix_to_face to the loss."""
+        fr = self._render(verts, faces, True)
+        return fr["pix_to_face"], fr["vis"]

@@ -56,7 +56,9 @@ class PostOptimizer:
         cam_pred (NB,7) [s,tx,ty,q]; masks (NB,H,W); edts_barrier (NB,1,H,W)|(NB,H,W); boundaries (NB,P,3);
         faces (NB|1,F,3); optical_flows (NB/T,T,H,W,2) already flipped and masked as predictor.py:334, or None.
         sample_indices (num_optim_iter, S) int64 boundary-point draws (default: torch.randperm per iteration, as the
-        reference).  Returns dict(pred_v, cam_pred, delta_v_res, losses (num_optim_iter,), mask_pred).
+        reference).  Returns dict(pred_v, cam_pred, delta_v_res, losses (num_optim_iter,), mask_pred): pred_v / cam_pred /
+        mask_pred are those of the LAST iteration's forward pass, i.e. before the last Adam step — what the reference keeps in
+        self.pred_v / self.cam_pred when its loop ends (predictor.py:309-349); delta_v_res is the optimised parameter.
 
         With use_cuda_graph the captured iteration is cached per input shape: later calls copy their inputs into the
         graph's static buffers, reset the Adam state and replay (capture + instantiation cost ~1 s, once)."""
@@ -109,7 +111,12 @@ class PostOptimizer:
     def _iteration(self, ctx):
         st = ctx["st"]
         ctx["sel_buf"].copy_(ctx["sel_all"].index_select(0, ctx["step_idx"])[0])
-        total, _, _, _ = self._objective(st, ctx["sel_buf"])
+        total, pred_v, cam, mask_pred = self._objective(st, ctx["sel_buf"])
+        out = ctx.get("out")
+        if out is None:   # static outputs (the first iteration always runs eagerly, before any capture)
+            out = ctx["out"] = dict(pred_v=torch.empty_like(pred_v), cam=torch.empty_like(cam), mask=torch.empty_like(mask_pred))
+        with torch.no_grad():   # what the loop leaves behind is the last forward pass, like the reference's self.pred_v
+            out["pred_v"].copy_(pred_v); out["cam"].copy_(cam); out["mask"].copy_(mask_pred)
         ctx["opt"].zero_grad(set_to_none=True)
         total.backward()
         ctx["opt"].step()
@@ -153,7 +160,22 @@ class PostOptimizer:
                 done = warm
             for _ in range(iters - done):
                 ctx["graph"].replay()
+        out = ctx["out"]
+        return dict(pred_v=out["pred_v"].clone(), cam_pred=out["cam"].clone(), delta_v_res=st["delta"].detach().clone(),
+                    losses=ctx["losses"].clone(), mask_pred=out["mask"].clone())
+
+    def first_gradient(self, mean_v, lbs, L, delta_v_res, cam_pred, masks, edts_barrier, boundaries, faces, sample_indices):
+        """The objective of the first iteration and its gradient w.r.t. the optimised parameters (no step taken): dict(loss,
+        delta[, scale, trans, quat]).  For parity checks: an Adam trajectory hides the gradient's scale."""
+        dev = mean_v.device
+        NB = delta_v_res.shape[0]
         with torch.no_grad():
-            _, pred_v, cam, mask_pred = self._objective(st, ctx["sel_all"][-1].contiguous())
-        return dict(pred_v=pred_v, cam_pred=cam, delta_v_res=st["delta"].detach().clone(), losses=ctx["losses"].clone(),
-                    mask_pred=mask_pred)
+            W = deform.skinning_matrix(lbs.detach(), L.detach())
+        faces_nb = faces if faces.shape[0] == NB else faces[:1].expand(NB, -1, -1)
+        inputs = dict(mean_v=mean_v.detach(), W=W, faces=faces_nb.contiguous(), masks=masks, edts=edts_barrier.reshape(NB, -1),
+                      boundaries=boundaries, cam=cam_pred.detach(), delta0=delta_v_res.detach(), sel=sample_indices.to(dev))
+        ctx = self._build(inputs, 1, False, dev)
+        total, _, _, _ = self._objective(ctx["st"], ctx["sel_all"][0].contiguous())
+        total.backward()
+        names = ["delta"] + (["scale", "trans", "quat"] if self.optimize_camera else [])
+        return dict(loss=total.detach(), **{k: ctx["st"][k].grad.clone() for k in names})

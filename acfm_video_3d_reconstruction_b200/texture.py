@@ -83,6 +83,14 @@ def render_textured(ndc, faces, textures, image_size, atlas=True):
         mode, tex = 0, textures.to(ndc.device)
     else:
         mode, tex = 1, (textures[None] if textures.dim() == 2 else textures)
+        if ndc.requires_grad and torch.is_grad_enabled():
+            # vertex-colour mode interpolates with the barycentrics: PyTorch3D would also send grad_bary / grad_zbuf of the IMAGE
+            # back to the vertices; here the vertices only receive the gradient that flows through dists (complete for `sil`,
+            # partial for `imgs`).  The reference never differentiates this mode (bird_vis.VisRenderer: visualisation only), so
+            # say so instead of being silently partial.
+            import warnings
+            warnings.warn("render_textured(atlas=False): d imgs / d vertices through the barycentric interpolation is not "
+                          "propagated (the silhouette's gradient is complete); detach the vertices for visualisation", stacklevel=2)
     rgba, p2f = _Textured.apply(ndc, faces, tex, int(image_size), mode)
     imgs = rgba[..., :3].permute(0, 3, 1, 2)
     return imgs, rgba[..., 3], p2f

@@ -41,8 +41,8 @@ WORKLOADS = {
     "C3": dict(template="horse", frames=64, G=8, handles=16, img=256, K=20, offset_z=0.0, full=True, clip_frames=16,
                desc="C3 multiframe quadruped step, one GPU's share: 4 clips x 16 frames x 8 cameras = 512 renders/GPU, 256x256, K=20, "
                     "16 handles; full loss set (camera assembly, mask l1 + edt, boundary, optical-flow, keypoint, hypothesis weighting)"),
-    "C4": dict(template="ico4", frames=4, G=2, handles=32, img=512, K=50, offset_z=0.0,
-               desc="C4 high-res stress: 2562v/5120f icosphere, 8 renders/GPU, 512x512, K=50"),
+    "C4": dict(template="ico4", frames=8, G=8, handles=32, img=512, K=50, offset_z=0.0,
+               desc="C4 high-res stress: 2562v/5120f subdivided template, 8 frames x 8 hypotheses = 64 renders/GPU, 512x512, K=50"),
 }
 W_EDT = 0.1  # edt_reg_wt-like weight on the edt term (any fixed weight exercises the same kernels)
 
@@ -136,6 +136,25 @@ class HotPath:
         self.h_gcams = torch.empty_like(wl.cams).pin_memory()
         if cfg.get("full"):
             self._full_inputs(rank)
+        self.bucket, self.side = None, None
+
+    def make_bucket(self, mbytes):
+        """A synthetic flat bucket standing for the gradients of the parameters shared by all frames (encoder, heads, texture
+        net: 12-15 M fp32 = 50-60 MB) — the model itself is out of scope, its all-reduce is not: the
+        bucket is summed over the ranks every step on a side stream, started when the backward starts."""
+        self.bucket = torch.zeros(int(mbytes * (1 << 20)) // 4, dtype=torch.float32, device=self.device) if mbytes > 0 else None
+        self.side = torch.cuda.Stream(device=self.device) if mbytes > 0 else None
+
+    def kick_bucket(self):
+        if self.bucket is None:
+            return
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            torch.distributed.all_reduce(self.bucket)
+
+    def join_bucket(self):
+        if self.bucket is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
 
     def _full_inputs(self, rank):
         """Device-resident synthetic targets of the full multiframe loss set: boundary points of the target
@@ -200,25 +219,30 @@ class HotPath:
             from acfm_video_3d_reconstruction_b200 import camera
             cam_pred = camera.assemble_cameras(cams, self.mirror, self.transforms, 0.05)
         pred_v, ndc = deform.deform_and_project(self.mean_v, W, delta, cam_pred, offset_z=cfg["offset_z"])
-        mask, p2f, _, _ = F_.soft_silhouette(ndc, self.faces, cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA,
-                                             want_vis=full)   # the boundary loss below takes the visibility from the render
-        ls = loss_utils.mask_losses(mask, target, edt)
+        # the render with the mask-loss sums fused into its epilogue (NeuralRenderer.forward_with_losses); the full loss set
+        # also takes the visible-vertex map from the render (the boundary loss below)
+        out = F_.soft_silhouette_losses(ndc, self.faces, cfg["img"], target, edt, F_.BLUR_SOFT, cfg["K"], F_.SIGMA, want_vis=full)
+        mask, p2f, sums = out[0], out[1], out[4]
+        ls = loss_utils.losses_from_sums(sums, cfg["img"] * cfg["img"])
         per = ls["l1"] + W_EDT * ls["edt"]
         if full:
             G, NB, T = cfg["G"], cfg["frames"], cfg["clip_frames"]
             self.vert2kp.grad = None
             pred_proj = F_.project(pred_v, cam_pred, 0.0)          # renderer.project_points (main.py:715), xy used in place
-            per = per + W_EDT * loss_utils.bds_loss(pred_proj, self.boundaries, self.faces, p2f, reduce=False, indices=self.bds_sel)
+            per = per + W_EDT * loss_utils.bds_loss(pred_proj, self.boundaries, self.faces, p2f, reduce=False, indices=self.bds_sel, visible=out[5])
             kp_verts = torch.softmax(self.vert2kp, dim=1).matmul(pred_v)                       # main.py:691-692
             per = per + loss_utils.kp_l2_loss(F_.project(kp_verts, cam_pred, 0.0), self.kps, reduction='none')
             of = loss_utils.optical_flow_loss(pred_v.repeat(G, 1, 1).reshape(G * NB // T, T, -1, 3),
                                               self.faces.expand(G * NB, -1, -1).reshape(G * NB // T, T, -1, 3), cam_pred, self.flows,
                                               self.of_renderer, None, reduce=False)[0]         # (G*B, T-1)
             per = per + 0.1 * of.mean(1).repeat_interleave(T)
-        total, _ = loss_utils.hypothesis_weighting(per.view(cfg["G"], cfg["frames"]))          # multiframe/main.py:735-746
+        total, _ = loss_utils.hypothesis_weighting(per.view(cfg["G"], delta.shape[0]))         # multiframe/main.py:735-746
+        if world > 1:
+            self.kick_bucket()             # the shared-parameter bucket travels while the backward runs
         total.backward()
         if world > 1:
             self.allreduce()
+            self.join_bucket()
         return total.detach(), delta.grad, cams.grad
 
     def allreduce(self):
@@ -241,6 +265,8 @@ def run_ours(args):
         torch.distributed.init_process_group("nccl", device_id=device)
     cfg = WORKLOADS[args.workload]
     hp = HotPath(cfg, rank, device)
+    if world > 1:
+        hp.make_bucket(args.shared_grad_mb)
     N_r = cfg["frames"] * cfg["G"]
     fwd_b, bwd_b = alg_bytes(cfg["img"], cfg["K"], hp.wl.V, hp.wl.F)
 
@@ -281,6 +307,20 @@ def run_ours(args):
     k_ms = [a[2].elapsed_time(b[2]) for a, b in zip(kev[0::2], kev[1::2]) if a[0] == "raster_fwd"]
     kb_ms = [a[2].elapsed_time(b[2]) for a, b in zip(kev[0::2], kev[1::2]) if a[0] == "raster_bwd"]
     clk = clocks.stop(t0, t1) if clocks else None
+    ms_nobucket, ar_check = None, None
+    if world > 1:
+        # the same K steps without the synthetic bucket (only the 82 KB lbs gradient is all-reduced), then the sums are checked
+        bucket, hp.bucket = hp.bucket, None
+        barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(args.steps):
+            hp.step(*dev_in, world=world)
+        n1.record()
+        barrier()
+        ms_nobucket = n0.elapsed_time(n1)
+        hp.bucket = bucket
+        ar_check = allreduce_check(hp, dev_in, rank, world, device)
     # ---- timed: end to end (pinned host -> device -> host) ----------------------------------------------------
     # The caller reads the loss every step, so the ~80 host-side launches of a step would sit on the critical path after each
     # synchronisation: the step is captured in a CUDA graph once (graphs.CapturedStep) and replayed; every step copies its
@@ -293,9 +333,12 @@ def run_ours(args):
         captured = graphs.CapturedStep(lambda d_, c_, t_, e_: hp.step(d_, c_, t_, e_, world=1), dev_in)
 
         def step_fn(*host):
+            if world > 1:
+                hp.kick_bucket()
             out = captured(*host)
             if world > 1:
                 hp.allreduce()                                      # lbs_param.grad lives in the graph's static memory
+                hp.join_bucket()
             return out
     except Exception as exc:  # capture is an optimisation, not a requirement
         e2e_mode = f"eager launches (graph capture failed: {type(exc).__name__})"
@@ -340,9 +383,12 @@ def run_ours(args):
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(args.steps):
+            if world > 1:
+                hp.kick_bucket()
             loss, gd, gc = pipe.run()
             if world > 1:
                 hp.allreduce()
+                hp.join_bucket()
             pipe.prefetch(*host_in)                                    # next step's inputs: overlaps this step's kernels
             hp.h_loss.copy_(loss, non_blocking=True)
             hp.h_gdelta.copy_(gd, non_blocking=True)
@@ -353,10 +399,11 @@ def run_ours(args):
         barrier()
         ms_e2e = g0.elapsed_time(g1)
         e2e_mode += "; inputs of step i+1 prefetched (pinned host -> device on a copy stream) during step i"
+    c3 = c3_side(args, rank, world, device) if args.workload == "C2" and not args.no_c3 else None
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_e2e_serial], device=device)
+        t = torch.tensor([ms, ms_e2e, ms_e2e_serial, ms_nobucket], device=device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms, ms_e2e, ms_e2e_serial = float(t[0]), float(t[1]), float(t[2])
+        ms, ms_e2e, ms_e2e_serial, ms_nobucket = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -390,6 +437,16 @@ def run_ours(args):
                                  "lists of pixels with mask == 0 or zero upstream gradient, so DRAM traffic is far below them"},
         "clocks": clk,
     }
+    if world > 1:
+        out["comm"] = {"per_step": f"NCCL all-reduce of the lbs gradient (82 KB) after the backward + a {args.shared_grad_mb} MB synthetic "
+                                   "shared-parameter bucket (SURVEY.md section 5: encoder / head gradients) all-reduced on a side stream "
+                                   "from the start of the backward",
+                       "shared_grad_mb": args.shared_grad_mb,
+                       "value_without_bucket": N_r * world * args.steps / (ms_nobucket * 1e-3),
+                       "ms_per_step_without_bucket": ms_nobucket / args.steps}
+        out["allreduce_check"] = ar_check
+    if c3 is not None:
+        out["c3"] = c3
     traffic = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic):
         try:
@@ -411,6 +468,75 @@ def run_ours(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def allreduce_check(hp, dev_in, rank, world, device):
+    """On-GPU correctness of the data-parallel step (SURVEY.md section 4 iv): (1) the all-reduced lbs gradient equals the sum
+    of the all-gathered per-rank gradients; (2) the bucket all-reduce sums a known pattern exactly; (3) for 2 ranks, the sharded
+    step equals ONE rank's step on the same global batch (the per-rank loss is a mean over the rank's frames, so the summed
+    gradient is `world` times the global-batch gradient)."""
+    dist = torch.distributed
+    hp.step(*dev_in, world=1)
+    g_local = hp.lbs_param.grad.detach().clone()
+    parts = [torch.empty_like(g_local) for _ in range(world)]
+    dist.all_gather(parts, g_local)
+    ref = torch.zeros_like(g_local)
+    for p_ in parts:
+        ref += p_
+    hp.step(*dev_in, world=world)
+    g_ar = hp.lbs_param.grad.detach().clone()
+    out = {"world": world, "grad_vs_gathered_sum_rel": float((g_ar - ref).abs().max() / ref.abs().max())}
+    if hp.bucket is not None:
+        hp.bucket.fill_(float(rank + 1))
+        dist.all_reduce(hp.bucket)
+        out["bucket_sum_exact"] = bool((hp.bucket == world * (world + 1) / 2).all())
+        hp.bucket.zero_()
+    if world == 2:
+        G, NB = hp.cfg["G"], hp.cfg["frames"]
+        gathered = []
+        for t in dev_in:
+            buf = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(buf, t.contiguous())
+            gathered.append(buf)
+        if rank == 0:
+            delta = torch.cat(gathered[0])
+            cams = torch.cat([torch.cat([c[g * NB:(g + 1) * NB] for c in gathered[1]]) for g in range(G)])   # hypothesis-major
+            hp.step(delta, cams, torch.cat(gathered[2]), torch.cat(gathered[3]), world=1)
+            g_one = hp.lbs_param.grad.detach()
+            out["sharded_vs_single_rank_rel"] = float((g_ar / world - g_one).abs().max() / g_one.abs().max())
+        dist.barrier()
+    return out
+
+
+def c3_side(args, rank, world, device):
+    """Side measurement at every N: BASELINE config 3's per-GPU share (full multiframe loss set), inputs resident, same
+    timing rules as the main line (barrier + synchronize around K steps, max over ranks)."""
+    cfg = WORKLOADS["C3"]
+    hp3 = HotPath(cfg, rank, device)
+    if world > 1:
+        hp3.make_bucket(args.shared_grad_mb)
+    dev_in = hp3.h2d()
+    for _ in range(max(3, args.warmup)):
+        hp3.step(*dev_in, world=world)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        hp3.step(*dev_in, world=world)
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t[0])
+    N_r = cfg["frames"] * cfg["G"]
+    return {"workload": cfg["desc"], "value": N_r * world * args.steps / (ms * 1e-3), "unit": "renders/s", "ms_per_step": ms / args.steps,
+            "n_gpus": world}
 
 
 def target_maps_bench(hp, cfg, peak, cpu=True, iters=10):
@@ -510,33 +636,61 @@ def correlation_bench(hp, peak, pairs=60, iters=20):
     return out
 
 
-def gpu_standin_bench(hp, cfg, renders=4):
-    """Side measurement: BASELINE.md's B-GPU-torch — a dense pure-PyTorch soft rasterizer (oracle/torch_dense.py, checked against
-    the C oracle in tests) on this same GPU, fwd + autograd bwd, on a bounded sample of the workload's renders.  A STAND-IN for
-    "PyTorch3D's CUDA path", which is not installable here; it does O(pixels x faces) work, PyTorch3D bins faces."""
+def gpu_standin_bench(hp, cfg):
+    """Side measurement: a STAND-IN for "the reference's PyTorch3D 0.3.0 CUDA path" on this same GPU, at the workload's FULL
+    size (512 renders at C2), raster fwd + bwd of the mask render: oracle/pt3d_cuda_standin.{cu,py} restates PyTorch3D's coarse
+    binning / one-thread-per-pixel fine / per-fragment-atomic backward kernels and runs the torch shader chain around them
+    (checked against the C oracle in tests/test_standin_gpu.py).  PyTorch3D itself cannot be installed here, so this — not
+    PyTorch3D — is the denominator that can be measured; two figures: max_faces_per_bin at the library default (the fine
+    kernel reads all 10000 slots of a bin per pixel) and tightened to what the mesh needs (what a careful user would pass).
+    The render half of OUR step (project + fused render fwd/bwd through the public API) is timed beside it."""
     from acfm_video_3d_reconstruction_b200 import functional as F_
-    from oracle import torch_dense
+    from oracle import pt3d_cuda_standin as sd
+    if not sd.available():
+        return {"unavailable": "oracle/_build/libacfm_pt3d_standin.so was not built"}
+    N = cfg["frames"] * cfg["G"]
+    S, K = cfg["img"], cfg["K"]
     with torch.no_grad():
-        X = hp.mean_v[None].repeat(renders, 1, 1)
-        ndc = F_.project(X, hp.h_cams[:renders].to(hp.device), cfg["offset_z"], -1.0, -1.0, F_.EYE_Z)
-    gm = torch.randn(renders, cfg["img"], cfg["img"], device=hp.device)
+        X = hp.mean_v[None].repeat(cfg["frames"], 1, 1)
+        ndc0 = F_.project(X, hp.h_cams.to(hp.device), cfg["offset_z"], -1.0, -1.0, F_.EYE_Z)
+    gm = torch.randn(N, S, S, device=hp.device)
+    faces1 = hp.faces[0]
 
-    def one(k):
-        nd = ndc[k:k + 1].clone().requires_grad_(True)
-        mask, _ = torch_dense.soft_silhouette(nd, hp.faces[0], cfg["img"], F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
-        (mask * gm[k:k + 1]).sum().backward()
+    def timed(fn, chunk, iters):
+        fn(0, chunk)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            for k in range(0, N, chunk):
+                fn(k, chunk)
+        e1.record()
+        torch.cuda.synchronize()
+        return N * iters / (e0.elapsed_time(e1) * 1e-3)
 
-    one(0)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(renders):
-        one(k)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    return {"value": renders / (ms * 1e-3), "unit": "renders/s", "kind": "stand-in (dense pure-PyTorch rasterizer, raster fwd+bwd only)",
-            "sample": f"{renders} renders of the workload, one at a time (each keeps ~10 GB of (pixels x faces) temporaries for autograd)"}
+    def standin(M):
+        def fn(k, c):
+            nd = ndc0[k:k + c].clone().requires_grad_(True)
+            mask, _ = sd.render_mask(nd, faces1, S, F_.BLUR_SOFT, K, F_.SIGMA, max_faces_per_bin=M)
+            (mask * gm[k:k + c]).sum().backward()
+        return fn
+
+    def ours(k, c):
+        nd = ndc0[k:k + c].clone().requires_grad_(True)
+        mask = F_.soft_silhouette(nd, hp.faces, S, F_.BLUR_SOFT, K, F_.SIGMA)[0]
+        (mask * gm[k:k + c]).sum().backward()
+
+    out = {"unit": "renders/s", "kind": "stand-in: PyTorch3D 0.3.0's CUDA rasterizer restated (oracle/pt3d_cuda_standin.cu, sm_100a -O3) + "
+                                         "its torch shader chain; raster fwd+bwd only",
+           "sample": f"all {N} renders of the workload"}
+    # the library default: max_faces_per_bin = max(10000, V_packed / 5); bin_faces alone is N*16*16*M*4 B -> chunks of 64 renders
+    out["default_max_faces_per_bin"] = timed(standin(None), 64, 1)
+    sd.render_mask(ndc0[:64], faces1, S, F_.BLUR_SOFT, K, F_.SIGMA, max_faces_per_bin=512, check_overflow=True)   # 512 slots do hold every bin
+    out["tight_max_faces_per_bin"] = timed(standin(512), 128, 2)
+    out["ours_same_call"] = timed(ours, N, 3)
+    out["value"] = out["tight_max_faces_per_bin"]
+    out["ours_over_standin"] = out["ours_same_call"] / out["value"]
+    return out
 
 
 def post_optimize_bench(hp, cfg, cpu=True, frames=12, iters=20):
@@ -693,6 +847,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shared-grad-mb", type=float, default=60.0,
+                    help="N>1: size of the synthetic shared-parameter gradient bucket all-reduced every step (0 = none)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 (full multiframe loss set) side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

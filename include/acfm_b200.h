@@ -80,14 +80,14 @@ int acfm_skin_bwd(const float* W, const float* delta, const float* grad_pred_v, 
 /* The skinning matrix itself, W = (L^T L + lbs lbs^T)^-1 lbs, for a Laplacian L that is constant across steps: replaces the
  * per-frame 642 x 642 factorisations of the reference block (repeat + bmm + torch.cholesky + torch.cholesky_solve,
  * multiframe/main.py:586-608) by a Woodbury update of Pinv = (L^T L + (c/V) 1 1^T)^-1, which the caller inverts ONCE
- * (fp64, (V,V) row-major; c = trace(L^T L) / V or any positive constant, passed as c_over_V = c / V).  fp64 arithmetic,
- * three kernels forward / five backward, deterministic reductions.  lbs (V,Kh) = softmax-over-vertices handle weights.
+ * (fp64, (V,V) row-major; c = trace(L^T L) / V or any positive constant, passed as c_over_V = c / V), together with its row sums
+ * Pinv_ones = Pinv 1 (V, fp64).  fp64 arithmetic, four kernels forward / seven backward, deterministic reductions, Kh <= 128.  lbs (V,Kh) = softmax-over-vertices handle weights.
  *   fwd: W (V,Kh) fp32.  The workspace (acfm_handle_solve_workspace_bytes, 16-byte aligned) keeps what the backward needs.
  *   bwd: grad_W (V,Kh) -> grad_lbs (V,Kh), with the workspace the matching fwd call filled.
  *   acfm_handle_solve_singular: 1 if that fwd call met a vanishing pivot (synchronises; for set-up checks and tests). */
 int64_t acfm_handle_solve_workspace_bytes(int V, int Kh);
-int acfm_handle_solve_fwd(const double* Pinv, const float* lbs, int V, int Kh, double c_over_V, float* W, void* workspace,
-                          int64_t workspace_bytes, void* stream);
+int acfm_handle_solve_fwd(const double* Pinv, const double* Pinv_ones, const float* lbs, int V, int Kh, double c_over_V, float* W,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 int acfm_handle_solve_bwd(const double* Pinv, const float* lbs, const float* grad_W, int V, int Kh, float* grad_lbs,
                           void* workspace, int64_t workspace_bytes, void* stream);
 int acfm_handle_solve_singular(const void* workspace, int V, int Kh, void* stream);
@@ -127,6 +127,25 @@ int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t 
                     float* bary, float* mask, float* visible_verts, void* workspace, int64_t workspace_bytes,
                     void* stream);
 int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W);
+
+/* The soft-silhouette render with the per-render mask losses fused into its epilogue: besides everything acfm_raster_fwd
+ * writes (K-deep fragments, mask, optional visible_verts), loss_sums (N,4) = { sum|m-t|, sum m t, sum (m+t-mt), sum edt m }
+ * over the pixels of each render — what l1_loss / iou / iou_loss / edt_loss reduce (multiframe/nnutils/loss_utils.py:18-32,
+ * 72-77,245-253; multiframe/main.py:644-645,715-716), identical to acfm_mask_sums_fwd on the rendered mask but without a
+ * second pass over it.  target, edt (NB,H,W) are read at render n % NB (the callers' .repeat(num_guesses,..)); edt may be
+ * NULL (sum 3 is then 0).  loss_workspace: acfm_raster_loss_workspace_bytes(), 16-byte aligned.  Deterministic (fixed-order
+ * reductions).  Backward: acfm_raster_soft_bwd_losses forms d loss / d mask on the fly from grad_sums (N,4) (plus an optional
+ * explicit grad_mask), so grad_mask is never materialised. */
+int64_t acfm_raster_loss_workspace_bytes(int N, int NB, int H, int W);
+int acfm_raster_fwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F,
+                           int H, int W, int K, float blur_radius, float sigma, int64_t* pix_to_face, float* zbuf, float* dists,
+                           float* mask, float* visible_verts, const float* target, const float* edt, int NB, float* loss_sums,
+                           void* loss_workspace, int64_t loss_workspace_bytes, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+int acfm_raster_soft_bwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                                int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
+                                const float* mask, const float* grad_mask, const float* grad_sums, const float* target,
+                                const float* edt, int NB, float* grad_ndc, const void* fwd_workspace, void* stream);
 
 /* Backward of rasterize_meshes + sigmoid_alpha_blend for the silhouette
  * (_C.rasterize_meshes_backward with grad only on dists).

@@ -65,12 +65,18 @@ def post_optimize(mean_v, lbs, L, delta_v_res, cam_pred, masks, edts_barrier, bo
         total = mask_loss_wt * mask_loss + boundaries_reg_wt * (bdt_reg_wt * edt_loss + edt_reg_wt * bdt_loss)
         return total, pred_v, cam, mask_pred
 
+    grad0 = None
     for it in range(sample_indices.shape[0]):
-        total, _, _, _ = objective(sample_indices[it])
+        total, pred_v, cam, mask_pred = objective(sample_indices[it])
         opt.zero_grad()
         total.backward()
+        if grad0 is None:   # the first iteration's gradient, for parity checks (an Adam trajectory hides its scale)
+            grad0 = dict(delta=dres.grad.clone())
+            if optimize_camera:
+                grad0.update(scale=scale.grad.clone(), trans=trans.grad.clone(), quat=quat.grad.clone())
         opt.step()
         losses.append(float(total.detach()))
-    with torch.no_grad():
-        _, pred_v, cam, mask_pred = objective(sample_indices[-1])
-    return dict(losses=np.asarray(losses), pred_v=pred_v, cam_pred=cam, delta_v_res=dres.detach(), mask_pred=mask_pred)
+    # like the reference (predictor.py:309-349), what is left when the loop ends is the LAST iteration's forward pass
+    # (self.pred_v / self.cam_pred / mask_pred before the last Adam step); the parameters themselves are one step further
+    return dict(losses=np.asarray(losses), pred_v=pred_v.detach(), cam_pred=cam.detach(), delta_v_res=dres.detach(),
+                mask_pred=mask_pred.detach(), grad0=grad0)

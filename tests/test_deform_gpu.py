@@ -119,8 +119,9 @@ def test_handle_solve_kernels_other_sizes(name, Kh):
     ws = solver.workspace(Kh)
     Wt = torch.empty(lbs.shape, device="cuda")
     lc = lbs.cuda().contiguous()
-    _lib.check(_lib.lib().acfm_handle_solve_fwd(_lib.ptr(solver.Pinv), _lib.ptr(lc), lc.shape[0], Kh, solver.c / solver.V, _lib.ptr(Wt),
-                                                _lib.ptr(ws), ws.numel(), _lib.stream_of(lc)), "acfm_handle_solve_fwd")
+    _lib.check(_lib.lib().acfm_handle_solve_fwd(_lib.ptr(solver.Pinv), _lib.ptr(solver.Pinv_ones), _lib.ptr(lc), lc.shape[0], Kh,
+                                                solver.c / solver.V, _lib.ptr(Wt), _lib.ptr(ws), ws.numel(), _lib.stream_of(lc)),
+               "acfm_handle_solve_fwd")
     assert _lib.lib().acfm_handle_solve_singular(_lib.ptr(ws), lc.shape[0], Kh, _lib.stream_of(lc)) == 0
     assert torch.equal(Wt, outs[0][0])
 

@@ -67,6 +67,27 @@ def test_full_size_batch(name, frames, G, S, K, offset_z):
         assert np.array_equal(got, want), f"pix_to_face of render {n}"
         assert np.array_equal(fr["zbuf"][n].cpu().numpy(), ref["zbuf"][i])
         assert np.array_equal(fr["dists"][n].cpu().numpy(), ref["dists"][i])
+    # depth ties (SURVEY.md section 9.9 i): how many covered pixels of the whole batch hold one, and — on the handful — that
+    # the reference's OTHER backend rule (PyTorch3D's CUDA kernels keep ties in traversal order, its CPU rasterizer orders
+    # them by face id like this kernel and the oracle) changes nothing away from those pixels
+    ties = cov = 0
+    for n in range(N):
+        z, v = fr["zbuf"][n], fr["pix_to_face"][n] >= 0
+        ties += int(((z[..., 1:] == z[..., :-1]) & v[..., 1:]).any(-1).sum())
+        cov += int(v[..., 0].sum())
+    print(f"{name} {S}x{S} K={K}: {ties} of {cov} covered pixels of the {N} renders hold an exact depth tie ({100.0 * ties / cov:.2f} %)")
+    assert ties / cov < 0.10
+    sub_ndc, sub_faces = ndc[pick].cpu().numpy(), np.repeat(wl.faces.numpy()[None], len(pick), 0)
+    orc.set_variant(tie_cuda=True)
+    try:
+        ref_cuda = orc.rasterize(sub_ndc, sub_faces, S, orc.BLUR_SOFT, K, want_bary=False)
+    finally:
+        orc.set_variant()
+    deeper = orc.rasterize(sub_ndc, sub_faces, S, orc.BLUR_SOFT, K + 1, want_bary=False)   # a tie can straddle the K-th slot
+    zd, vd = deeper["zbuf"], deeper["pix_to_face"] >= 0
+    tie_px = ((zd[..., 1:] == zd[..., :-1]) & vd[..., 1:]).any(-1)
+    differs = (ref_cuda["pix_to_face"] != ref["pix_to_face"]).any(-1) | (ref_cuda["dists"] != ref["dists"]).any(-1)
+    assert not (differs & ~tie_px).any()
     # batch invariance: the same renders on their own, in another order
     sub = list(reversed(pick))
     alone = F_.rasterize(ndc[sub].contiguous(), faces, S, F_.BLUR_SOFT, K, sigma=F_.SIGMA, want_mask=True)

@@ -51,6 +51,15 @@ def test_post_optimizer_vs_cpu_restatement(optimize_camera):
         assert abs(l[0] - ref["losses"][0]) <= 2e-4 * ref["losses"][0], (graph, l, ref["losses"])
         assert np.allclose(l, ref["losses"], rtol=5e-3, atol=0), (graph, l, ref["losses"])
         assert np.abs(outs[graph]["mask_pred"].cpu().numpy() - ref["mask_pred"].numpy()).mean() < 1e-3
+        # the returned geometry is the last iteration's forward pass (before the last step), as in the reference
+        assert util.rel_err(outs[graph]["pred_v"].cpu().numpy(), ref["pred_v"].numpy()) < 2e-3
+    # one iteration's gradient (an Adam trajectory hides the gradient's scale): 1e-3 relative per parameter group
+    g = PostOptimizer(img_size=d["S"], num_optim_iter=1, optimize_camera=optimize_camera, of_loss_wt=0.0, use_cuda_graph=False
+                      ).first_gradient(c["mean_v"], c["lbs"], c["L"], c["delta"], c["cam"], c["masks"], c["edts"], c["bds"],
+                                       c["faces"], c["sel"])
+    assert abs(float(g["loss"]) - ref["losses"][0]) <= 2e-4 * ref["losses"][0]
+    for k, gr in ref["grad0"].items():
+        assert util.rel_err(g[k].cpu().numpy(), gr.numpy()) < 1e-3, k
     assert ref["losses"][-1] < ref["losses"][0]                                  # the loop does optimise
     assert np.allclose(outs[True]["losses"].cpu().numpy(), outs[False]["losses"].cpu().numpy(), rtol=1e-4)
 
