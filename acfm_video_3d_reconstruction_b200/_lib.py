@@ -35,10 +35,10 @@ SIGNATURES = {
                         _c_int, _c_f, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp],
     "acfm_raster_fwd_workspace_bytes": [_c_int, _c_int, _c_int],
     "acfm_raster_loss_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
-    "acfm_raster_fwd_losses": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp,
-                               _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp],
-    "acfm_raster_soft_bwd_losses": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp, _c_vp,
-                                    _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp],
+    "acfm_raster_fwd_train": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp,
+                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp],
+    "acfm_raster_soft_bwd_train": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp, _c_vp,
+                                   _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp],
     "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_dists_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,

@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
     }
     if (vec) {
       // fragments in groups of four (16-byte loads, all issued before use); lanes start at different groups so that
-      // neighbouring pixels, which see the same faces at the same depth rank, touch different vertices at the same time
+      // neighbouring pixels, which see the same faces at the same depth rank, touch different vertices at the same time.
+      // (Measured without gain: combining the lanes that hit the same vertex with __match_any_sync + __reduce_add_sync before
+      // the shared atomics — 0.63 -> 1.98 ms at C2, the match is far slower than the conflicts it removes; saving the closest
+      // edge per fragment in the forward so that one foot point is computed instead of three — 0.64 -> 0.63 ms for +0.07 ms
+      // of forward: the kernel waits on fragment loads and shared atomics, not on arithmetic.)
       const int groups = K >> 2;
       int g = lane % groups;
       for (int s = 0; s < groups; ++s) {
@@ -271,8 +275,11 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
           if (gd == 0.0f) continue;
           if (signbit(d)) gd = -gd;  // dist = inside ? -|d| : |d|
           const ushort4 iv = sfaces[(int)(fid[e] - nF)];
-          if (FROM_MASK) frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accx);
-          else frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accl);
+          if (FROM_MASK) {
+            frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accx);
+          } else {
+            frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accl);
+          }
         }
       }
     } else {
@@ -353,11 +360,12 @@ extern "C" int acfm_raster_soft_bwd(const float* ndc, const void* faces, int fac
                     pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, fwd_workspace, stream);
 }
 
-extern "C" int acfm_raster_soft_bwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
-                                           int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
-                                           const float* mask, const float* grad_mask, const float* grad_sums, const float* target,
-                                           const float* edt, int NB, float* grad_ndc, const void* fwd_workspace, void* stream) {
-  return launch_bwd("acfm_raster_soft_bwd_losses", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma,
+extern "C" int acfm_raster_soft_bwd_train(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                                          int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
+                                          const float* mask, const float* grad_mask, const float* grad_sums,
+                                          const float* target, const float* edt, int NB, float* grad_ndc, const void* fwd_workspace,
+                                          void* stream) {
+  return launch_bwd("acfm_raster_soft_bwd_train", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma,
                     pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, fwd_workspace, stream, grad_sums, target, edt, NB);
 }
 

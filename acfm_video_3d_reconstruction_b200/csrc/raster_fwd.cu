@@ -7,12 +7,14 @@
 // inside / blur / depth decisions) is computed in strict IEEE fp32 in the CPU reference's operator
 // order, so pix_to_face, zbuf and dists are bit-identical to oracle/.
 //
-// Three kernels per call when the caller passes a workspace (the split path, further down in this file):
-//   raster_prep_kernel   one CTA per render: mesh bounding box -> live regions (filed heaviest first by face count, so
-//                        the rasterizer's grid ends on light regions) and runs of empty regions;
-//   raster_fill_kernel   second stream: the -1 padding of the empty regions (87% of all fragment bytes at the reference's
-//                        workloads) written by the TMA unit with cp.async.bulk shared -> global stores, concurrently;
-//   raster_fwd_kernel    one CTA per LIVE (render, 32x32-pixel region), described below.
+// Three kernels per call when the caller passes a workspace (the split path, further down in this file), all on the caller's
+// stream:
+//   raster_prep_kernel   one CTA per render: mesh bounding box -> live regions (filed heaviest first by face count, so the
+//                        rasterizer's grid ends on light regions) and runs of empty regions;
+//   raster_fill_kernel   the -1 padding of the empty regions (87% of all fragment bytes at the reference's workloads), written
+//                        by the TMA unit with cp.async.bulk shared -> global stores from one one-warp CTA per SM;
+//   raster_fwd_kernel    one CTA per LIVE (render, 32x32-pixel region), described below — dispatched beside the padding kernel
+//                        by programmatic dependent launch as soon as the padding CTAs are in place.
 // Without a workspace raster_fwd_kernel runs on every region and pads the empty ones itself.
 //
 // raster_fwd_kernel, one CTA per (render, 32x32-pixel region):
@@ -31,11 +33,11 @@
 //          survivors' record ids are pushed on a per-lane queue;
 //      (c) evaluate, lane = pixel, face per lane: each lane pops ITS OWN queue, so lanes only spend
 //          instructions on (pixel, face) pairs that are real candidates (the face-uniform evaluation
-//          of (b)'s survivors would run at ~30% lane utilisation); the exact §9.4 test, then sorted
-//          insertion into the lane's K-nearest list (shared memory, [lane][K|1] layout: conflict-free
-//          both for the lane-private insertions and for the pixel-major output pass);
-//      (d) blend the silhouette in depth order and write pix_to_face / zbuf / dists with 16-byte
-//          stores straight from the lists.
+//          of (b)'s survivors would run at ~30% lane utilisation); the exact §9.4 test — left right after the depth when the
+//          fragment can no longer enter the pixel's full set — then the fragment joins the lane's K-nearest SET (K = 20:
+//          unsorted, append or replace-the-farthest, no shifting; other K: round 1's sorted list) in shared memory;
+//      (d) one rank pass puts every lane's set in depth order (K = 20), the silhouette is blended in that order, the fused
+//          mask-loss sums are accumulated, and pix_to_face / zbuf / dists are written with 16-byte stores.
 //   Region faces beyond `cap` (meshes that are tiny on screen) go through a slower face-uniform path
 //   with on-the-fly set-up broadcast by warp shuffles.
 //
@@ -792,7 +794,10 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         if (cand) queue[(qn++) * 32 + lane] = (unsigned char)jj;
         full = __any_sync(0xffffffffu, qn == kQueue);
       }
-      // (c) evaluate: each lane pops its own queue (prefetching the next entry's record a round early measured no gain)
+      // (c) evaluate: each lane pops its own queue.  (Measured without gain: prefetching the next entry's record a round early;
+      // letting a lane with an empty queue evaluate a candidate of its mirror lane (lane ^ 31) and hand the result back by
+      // shuffles — 20 % fewer rounds in scripts/sim_lanes.py, but 2.41 -> 2.50 ms at C2: the shuffles, the selects and the
+      // second add per round cost more than the idle lanes did.)
       const int qmax = __reduce_max_sync(0xffffffffu, qn);
       for (int i = 0; i < qmax; ++i) {
         if (i < qn) {
@@ -1393,16 +1398,17 @@ extern "C" int64_t acfm_raster_loss_workspace_bytes(int N, int NB, int H, int W)
   return 16 * (int64_t)N * ((W + kRegion - 1) / kRegion) * ((H + kRegion - 1) / kRegion) + 8 * (int64_t)NB;
 }
 
-extern "C" int acfm_raster_fwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
-                                      int F, int H, int W, int K, float blur_radius, float sigma, int64_t* pix_to_face, float* zbuf,
-                                      float* dists, float* mask, float* visible_verts, const float* target, const float* edt, int NB,
-                                      float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes, void* workspace,
-                                      int64_t workspace_bytes, void* stream) {
-  ACFM_REQUIRE(target && loss_sums && loss_workspace && mask, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_losses: null pointer");
-  ACFM_REQUIRE(NB > 0 && N % NB == 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_losses: N=%d is not a multiple of NB=%d", N, NB);
+extern "C" int acfm_raster_fwd_train(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                                     int F, int H, int W, int K, float blur_radius, float sigma, int64_t* pix_to_face, float* zbuf,
+                                     float* dists, float* mask, float* visible_verts, const float* target,
+                                     const float* edt, int NB, float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
+  ACFM_REQUIRE(mask, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_train: null mask pointer");
+  ACFM_REQUIRE(!loss_sums || (target && loss_workspace), ACFM_ERR_BAD_ARG, "acfm_raster_fwd_train: loss_sums needs target and loss_workspace");
+  ACFM_REQUIRE(!loss_sums || (NB > 0 && N % NB == 0), ACFM_ERR_BAD_ARG, "acfm_raster_fwd_train: N=%d is not a multiple of NB=%d", N, NB);
   return raster_fwd_impl(ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, blur_radius, 0, 0, sigma, pix_to_face, zbuf,
-                         dists, nullptr, mask, visible_verts, target, edt, NB, loss_sums, loss_workspace, loss_workspace_bytes,
-                         workspace, workspace_bytes, stream);
+                         dists, nullptr, mask, visible_verts, loss_sums ? target : nullptr, loss_sums ? edt : nullptr, NB, loss_sums,
+                         loss_workspace, loss_workspace_bytes, workspace, workspace_bytes, stream);
 }
 
 namespace {
@@ -1433,7 +1439,11 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
   p.vec_ok = ((((uintptr_t)pix_to_face) | ((uintptr_t)zbuf) | ((uintptr_t)dists)) & 15u) == 0;
   int smem = 0, cap = 0;
   const int nw = fwd_config(V, F, K, &smem, &cap);
-  ACFM_REQUIRE(nw > 0, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: needs more than 232448 B of shared memory for V=%d F=%d K=%d", V, F, K);
+  // the render's vertices (12 V bytes) and face list (4 F) are staged in one CTA's shared memory: meshes up to about
+  // 12 V + 4 F <= 190 KB (e.g. 10 k vertices / 20 k faces) at K = 20; the 16-bit face ids allow 65 535 of each at most
+  ACFM_REQUIRE(nw > 0, ACFM_ERR_UNSUPPORTED,
+               "acfm_raster_fwd: V=%d F=%d K=%d needs more than the 232448 B of shared memory of one CTA (12 V + 4 F bytes of staged "
+               "mesh + the per-pixel sets: about V <= 10000 / F <= 20000 at K = 20)", V, F, K);
   p.cap = cap;
   p.work = nullptr;
   const long long ctas = (long long)N * p.regions_x * p.regions_y;
@@ -1443,7 +1453,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
   if (loss_sums) {
     // fused losses: region partials (zero where nothing is rendered) + per-target base sums, both in the caller's scratch
     ACFM_REQUIRE(loss_workspace_bytes >= 16 * ctas + 8 * (long long)NB && (((uintptr_t)loss_workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
-                 "acfm_raster_fwd_losses: loss workspace must be 16-byte aligned and hold acfm_raster_loss_workspace_bytes()");
+                 "acfm_raster_fwd_train: loss workspace must be 16-byte aligned and hold acfm_raster_loss_workspace_bytes()");
     p.loss_part = (float*)loss_workspace;
     ACFM_CUDA_OK(cudaMemsetAsync(p.loss_part, 0, 16 * (size_t)ctas, st));
     loss_target_base_kernel<<<NB, 256, 0, st>>>(loss_target, H * W, p.loss_part + 4 * ctas);

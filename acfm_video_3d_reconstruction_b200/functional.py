@@ -135,13 +135,79 @@ def rasterize(ndc, faces, image_size, blur_radius, faces_per_pixel, clip_barycen
     return dict(pix_to_face=p2f, zbuf=zbuf, dists=dists, bary=bary, mask=mask, vis=vis, work=ws)
 
 
+def _train_render(ndc, faces, image_size, blur_radius, K, sigma, want_vis, target=None, edt=None):
+    """acfm_raster_fwd_train: the render a training step differentiates — fragments, mask, optionally the visible-vertex map
+    and the fused mask-loss sums.  Returns a dict."""
+    _lib.require_cuda(ndc, faces, target, edt)
+    ndc = _f32c(ndc)
+    N, V, _ = ndc.shape
+    H = W = int(image_size)
+    fa, i64, fstride, F = _faces_arg(faces, N)
+    dev = ndc.device
+    NB = 0
+    if target is not None:
+        target = _f32c(target)
+        edt = _f32c(edt) if edt is not None else None
+        NB = target.shape[0]
+        if N and (NB == 0 or N % NB or target.numel() != NB * H * W or (edt is not None and edt.numel() != target.numel())):
+            raise ValueError(f"renders {N} vs target {tuple(target.shape)}: the batch must divide, the pixels must match")
+    p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
+    zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+    dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+    mask = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+    sums = torch.empty((N, 4), dtype=torch.float32, device=dev) if target is not None else None
+    vis = torch.empty((N, V), dtype=torch.float32, device=dev) if want_vis else None
+    L = _lib.lib()
+    ws_bytes = int(L.acfm_raster_fwd_workspace_bytes(N, H, W)) if SPLIT_FILL else 0
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+    lw_bytes = int(L.acfm_raster_loss_workspace_bytes(N, max(NB, 1), H, W)) if target is not None else 0
+    lw = torch.empty((max(lw_bytes, 16),), dtype=torch.uint8, device=dev) if target is not None else None
+    if _lib.event_hook is not None:
+        _lib.event_hook("raster_fwd", 0)
+    if N:
+        with torch.cuda.device(dev):
+            st = L.acfm_raster_fwd_train(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K, float(blur_radius), float(sigma),
+                                         _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(vis),
+                                         _lib.ptr(target), _lib.ptr(edt), NB, _lib.ptr(sums), _lib.ptr(lw), lw_bytes, _lib.ptr(ws),
+                                         ws_bytes, _lib.stream_of(ndc))
+        _lib.check(st, "acfm_raster_fwd_train")
+        # prep + padding + rasterizer (or the one kernel), + target base and reduce for the fused sums, + the visibility memset
+        _lib.count((3 if ws is not None else 1) + (2 if sums is not None else 0) + (1 if vis is not None else 0))
+    if _lib.event_hook is not None:
+        _lib.event_hook("raster_fwd", 1)
+    return dict(ndc=ndc, pix_to_face=p2f, zbuf=zbuf, dists=dists, mask=mask, sums=sums, vis=vis, work=ws, target=target, edt=edt)
+
+
+def _train_render_bwd(saved, cfg, work, grad_mask, grad_sums):
+    ndc, faces, p2f, dists, mask, target, edt = saved
+    S, K, sigma = cfg
+    N, V, _ = ndc.shape
+    fa, i64, fstride, F = _faces_arg(faces, N)
+    grad_mask = _f32c(grad_mask) if grad_mask is not None else None
+    grad_sums = _f32c(grad_sums) if grad_sums is not None else None
+    g = torch.empty_like(ndc)
+    if _lib.event_hook is not None:
+        _lib.event_hook("raster_bwd", 0)
+    with torch.cuda.device(ndc.device):
+        st = _lib.lib().acfm_raster_soft_bwd_train(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma, _lib.ptr(p2f),
+                                                   _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(grad_mask),
+                                                   _lib.ptr(grad_sums), _lib.ptr(target), _lib.ptr(edt),
+                                                   target.shape[0] if target is not None else 1, _lib.ptr(g), _lib.ptr(work),
+                                                   _lib.stream_of(ndc))
+    _lib.check(st, "acfm_raster_soft_bwd_train")
+    _lib.count(2)  # memset + kernel
+    if _lib.event_hook is not None:
+        _lib.event_hook("raster_bwd", 1)
+    return g
+
+
 class _SoftSilhouette(torch.autograd.Function):
-    """ndc (N,V,3) -> mask (N,H,W), pix_to_face, zbuf, dists; differentiable in ndc through dists."""
+    """ndc (N,V,3) -> mask (N,H,W), pix_to_face, zbuf, dists [, vis]; differentiable in ndc through dists."""
 
     @staticmethod
     def forward(ctx, ndc, faces, image_size, blur_radius, K, sigma, want_vis=False):
-        fr = rasterize(ndc, faces, image_size, blur_radius, K, sigma=sigma, want_mask=True, want_vis=want_vis)
-        ctx.save_for_backward(ndc.contiguous(), faces, fr["pix_to_face"], fr["dists"], fr["mask"])
+        fr = _train_render(ndc, faces, image_size, blur_radius, K, sigma, want_vis)
+        ctx.save_for_backward(fr["ndc"], faces, fr["pix_to_face"], fr["dists"], fr["mask"])
         ctx.cfg = (int(image_size), int(K), float(sigma))
         ctx.work = fr["work"]   # the forward's region work lists: the backward visits the live regions only, heaviest first
         ctx.mark_non_differentiable(fr["pix_to_face"], fr["zbuf"], fr["dists"])
@@ -153,24 +219,9 @@ class _SoftSilhouette(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_mask, _g1, _g2, _g3, _g4=None):
-        ndc, faces, p2f, dists, mask = ctx.saved_tensors
-        S, K, sigma = ctx.cfg
-        N, V, _ = ndc.shape
-        fa, i64, fstride, F = _faces_arg(faces, N)
-        if grad_mask is None:
+        if grad_mask is None or ctx.saved_tensors[0].shape[0] == 0:
             return None, None, None, None, None, None, None
-        grad_mask = _f32c(grad_mask)
-        g = torch.empty_like(ndc)
-        if _lib.event_hook is not None:
-            _lib.event_hook("raster_bwd", 0)
-        with torch.cuda.device(ndc.device):
-            st = _lib.lib().acfm_raster_soft_bwd(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma,
-                                                 _lib.ptr(p2f), _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(grad_mask),
-                                                 _lib.ptr(g), _lib.ptr(ctx.work), _lib.stream_of(ndc))
-        _lib.check(st, "acfm_raster_soft_bwd")
-        _lib.count(2)  # memset + kernel
-        if _lib.event_hook is not None:
-            _lib.event_hook("raster_bwd", 1)
+        g = _train_render_bwd(ctx.saved_tensors + (None, None), ctx.cfg, ctx.work, grad_mask, None)
         return g, None, None, None, None, None, None
 
 
@@ -182,79 +233,30 @@ def soft_silhouette(ndc, faces, image_size, blur_radius=BLUR_SOFT, faces_per_pix
 
 
 class _SoftSilhouetteLosses(torch.autograd.Function):
-    """The soft-silhouette render with the per-render mask-loss sums fused in (acfm_raster_fwd_losses / _soft_bwd_losses):
+    """The soft-silhouette render with the per-render mask-loss sums fused in (acfm_raster_fwd_train / _soft_bwd_train):
     ndc (N,V,3), target (NB,H,W), edt (NB,H,W) or None -> mask, pix_to_face, zbuf, dists, sums (N,4) [, vis].
     Differentiable in ndc through BOTH the mask and the sums; d loss / d mask of the sums is formed inside the rasterizer
     backward and never materialised."""
 
     @staticmethod
     def forward(ctx, ndc, faces, target, edt, image_size, blur_radius, K, sigma, want_vis):
-        _lib.require_cuda(ndc, faces, target, edt)
-        ndc, target = _f32c(ndc), _f32c(target)
-        edt = _f32c(edt) if edt is not None else None
-        N, V, _ = ndc.shape
-        H = W = int(image_size)
-        NB = target.shape[0]
-        if N and (NB == 0 or N % NB or target.numel() != NB * H * W or (edt is not None and edt.numel() != target.numel())):
-            raise ValueError(f"renders {N} vs target {tuple(target.shape)}: the batch must divide, the pixels must match")
-        fa, i64, fstride, F = _faces_arg(faces, N)
-        dev = ndc.device
-        p2f = torch.empty((N, H, W, K), dtype=torch.int64, device=dev)
-        zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-        dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-        mask = torch.empty((N, H, W), dtype=torch.float32, device=dev)
-        sums = torch.empty((N, 4), dtype=torch.float32, device=dev)
-        vis = torch.empty((N, V), dtype=torch.float32, device=dev) if want_vis else None
-        L = _lib.lib()
-        ws_bytes = int(L.acfm_raster_fwd_workspace_bytes(N, H, W))
-        ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
-        lw_bytes = int(L.acfm_raster_loss_workspace_bytes(N, max(NB, 1), H, W))
-        lw = torch.empty((max(lw_bytes, 16),), dtype=torch.uint8, device=dev)
-        if _lib.event_hook is not None:
-            _lib.event_hook("raster_fwd", 0)
-        if N:
-            with torch.cuda.device(dev):
-                st = L.acfm_raster_fwd_losses(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K, float(blur_radius),
-                                              float(sigma), _lib.ptr(p2f), _lib.ptr(zbuf), _lib.ptr(dists), _lib.ptr(mask),
-                                              _lib.ptr(vis), _lib.ptr(target), _lib.ptr(edt), NB, _lib.ptr(sums), _lib.ptr(lw),
-                                              lw_bytes, _lib.ptr(ws), ws_bytes, _lib.stream_of(ndc))
-            _lib.check(st, "acfm_raster_fwd_losses")
-            _lib.count(5 + (1 if vis is not None else 0))  # prep, padding, rasterizer, target base, reduce
-        if _lib.event_hook is not None:
-            _lib.event_hook("raster_fwd", 1)
-        ctx.save_for_backward(ndc, faces, p2f, dists, mask, target, edt)
-        ctx.cfg = (H, int(K), float(sigma))
-        ctx.work = ws
-        ctx.mark_non_differentiable(p2f, zbuf, dists)
+        fr = _train_render(ndc, faces, image_size, blur_radius, K, sigma, want_vis, target, edt)
+        ctx.save_for_backward(fr["ndc"], faces, fr["pix_to_face"], fr["dists"], fr["mask"], fr["target"], fr["edt"])
+        ctx.cfg = (int(image_size), int(K), float(sigma))
+        ctx.work = fr["work"]
+        ctx.mark_non_differentiable(fr["pix_to_face"], fr["zbuf"], fr["dists"])
         ctx.set_materialize_grads(False)
         if want_vis:
-            ctx.mark_non_differentiable(vis)
-            return mask, p2f, zbuf, dists, sums, vis
-        return mask, p2f, zbuf, dists, sums
+            ctx.mark_non_differentiable(fr["vis"])
+            return fr["mask"], fr["pix_to_face"], fr["zbuf"], fr["dists"], fr["sums"], fr["vis"]
+        return fr["mask"], fr["pix_to_face"], fr["zbuf"], fr["dists"], fr["sums"]
 
     @staticmethod
     def backward(ctx, grad_mask, _g1, _g2, _g3, grad_sums, _g5=None):
-        ndc, faces, p2f, dists, mask, target, edt = ctx.saved_tensors
-        S, K, sigma = ctx.cfg
-        N, V, _ = ndc.shape
         none = (None,) * 9
-        if (grad_mask is None and grad_sums is None) or N == 0:
+        if (grad_mask is None and grad_sums is None) or ctx.saved_tensors[0].shape[0] == 0:
             return none
-        fa, i64, fstride, F = _faces_arg(faces, N)
-        grad_mask = _f32c(grad_mask) if grad_mask is not None else None
-        grad_sums = _f32c(grad_sums) if grad_sums is not None else None
-        g = torch.empty_like(ndc)
-        if _lib.event_hook is not None:
-            _lib.event_hook("raster_bwd", 0)
-        with torch.cuda.device(ndc.device):
-            st = _lib.lib().acfm_raster_soft_bwd_losses(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma,
-                                                        _lib.ptr(p2f), _lib.ptr(dists), _lib.ptr(mask), _lib.ptr(grad_mask),
-                                                        _lib.ptr(grad_sums), _lib.ptr(target), _lib.ptr(edt), target.shape[0],
-                                                        _lib.ptr(g), _lib.ptr(ctx.work), _lib.stream_of(ndc))
-        _lib.check(st, "acfm_raster_soft_bwd_losses")
-        _lib.count(2)  # memset + kernel
-        if _lib.event_hook is not None:
-            _lib.event_hook("raster_bwd", 1)
+        g = _train_render_bwd(ctx.saved_tensors, ctx.cfg, ctx.work, grad_mask, grad_sums)
         return (g,) + none[1:]
 
 

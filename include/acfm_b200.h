@@ -128,24 +128,26 @@ int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t 
                     void* stream);
 int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W);
 
-/* The soft-silhouette render with the per-render mask losses fused into its epilogue: besides everything acfm_raster_fwd
- * writes (K-deep fragments, mask, optional visible_verts), loss_sums (N,4) = { sum|m-t|, sum m t, sum (m+t-mt), sum edt m }
- * over the pixels of each render — what l1_loss / iou / iou_loss / edt_loss reduce (multiframe/nnutils/loss_utils.py:18-32,
- * 72-77,245-253; multiframe/main.py:644-645,715-716), identical to acfm_mask_sums_fwd on the rendered mask but without a
- * second pass over it.  target, edt (NB,H,W) are read at render n % NB (the callers' .repeat(num_guesses,..)); edt may be
- * NULL (sum 3 is then 0).  loss_workspace: acfm_raster_loss_workspace_bytes(), 16-byte aligned.  Deterministic (fixed-order
- * reductions).  Backward: acfm_raster_soft_bwd_losses forms d loss / d mask on the fly from grad_sums (N,4) (plus an optional
- * explicit grad_mask), so grad_mask is never materialised. */
+/* The soft-silhouette render as a TRAINING step uses it (forward that will be differentiated): everything acfm_raster_fwd
+ * writes (K-deep fragments, mask, optional visible_verts) plus, fused into its epilogue,
+ *   loss_sums (N,4) or NULL = { sum|m-t|, sum m t, sum (m+t-mt), sum edt m } over the pixels of each render — what l1_loss / iou /
+ *     iou_loss / edt_loss reduce (multiframe/nnutils/loss_utils.py:18-32,72-77,245-253; multiframe/main.py:644-645,715-716),
+ *     identical to acfm_mask_sums_fwd on the rendered mask but accumulated in the render's epilogue.  target, edt (NB,H,W) are
+ *     read at render n % NB (the callers' .repeat(num_guesses,..)); edt may be NULL (sum 3 is then 0).  loss_workspace:
+ *     acfm_raster_loss_workspace_bytes(), 16-byte aligned.  Deterministic (fixed-order reductions).
+ * Backward: acfm_raster_soft_bwd_train takes d loss / d mask as an explicit grad_mask (N,H,W) and / or as grad_sums (N,4), from
+ * which it forms d loss / d mask on the fly — a loss computed from loss_sums never materialises grad_mask. */
 int64_t acfm_raster_loss_workspace_bytes(int N, int NB, int H, int W);
-int acfm_raster_fwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F,
-                           int H, int W, int K, float blur_radius, float sigma, int64_t* pix_to_face, float* zbuf, float* dists,
-                           float* mask, float* visible_verts, const float* target, const float* edt, int NB, float* loss_sums,
-                           void* loss_workspace, int64_t loss_workspace_bytes, void* workspace, int64_t workspace_bytes,
-                           void* stream);
-int acfm_raster_soft_bwd_losses(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
-                                int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
-                                const float* mask, const float* grad_mask, const float* grad_sums, const float* target,
-                                const float* edt, int NB, float* grad_ndc, const void* fwd_workspace, void* stream);
+int acfm_raster_fwd_train(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F,
+                          int H, int W, int K, float blur_radius, float sigma, int64_t* pix_to_face, float* zbuf, float* dists,
+                          float* mask, float* visible_verts, const float* target, const float* edt, int NB,
+                          float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+int acfm_raster_soft_bwd_train(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                               int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
+                               const float* mask, const float* grad_mask, const float* grad_sums,
+                               const float* target, const float* edt, int NB, float* grad_ndc, const void* fwd_workspace,
+                               void* stream);
 
 /* Backward of rasterize_meshes + sigmoid_alpha_blend for the silhouette
  * (_C.rasterize_meshes_backward with grad only on dists).

@@ -33,8 +33,12 @@ class _SoftRender(torch.autograd.Function):
 
 def post_optimize(mean_v, lbs, L, delta_v_res, cam_pred, masks, edts_barrier, boundaries, faces, sample_indices, img_size,
                   offset_z=0.0, lr=5e-3, mask_loss_wt=1.0, boundaries_reg_wt=1.0, edt_reg_wt=0.1, bdt_reg_wt=0.1,
-                  optimize_camera=False):
-    """All tensors torch CPU (fp32); faces (NB,F,3) int64.  Returns dict(losses, pred_v, cam_pred, delta_v_res, mask_pred)."""
+                  optimize_camera=False, solve_dtype=torch.float32):
+    """All tensors torch CPU (fp32); faces (NB,F,3) int64.  Returns dict(losses, pred_v, cam_pred, delta_v_res, mask_pred, grad0).
+    solve_dtype=torch.float64 runs the handle solve in double (the reference's fp32 batched Cholesky carries ~3e-5 absolute
+    vertex error and ~2e-3 relative gradient error at cond ~1e3): the truth for gradient checks."""
+    f32 = torch.float32
+    mean_v, lbs, L = mean_v.to(solve_dtype), lbs.to(solve_dtype), L.to(solve_dtype)
     NB = delta_v_res.shape[0]
     A = lbs.t()[None].repeat(NB, 1, 1)                                   # self.lbs (predictor.py:257-258)
     mean = mean_v[None].repeat(NB, 1, 1)
@@ -54,9 +58,9 @@ def post_optimize(mean_v, lbs, L, delta_v_res, cam_pred, masks, edts_barrier, bo
 
     def objective(sel):
         cam = torch.cat([scale, trans, torch.nn.functional.normalize(quat, dim=-1)], 1) if optimize_camera else cam_pred
-        delta_v = delta_v_ms + dres
+        delta_v = delta_v_ms + dres.to(solve_dtype)
         b = Lb.permute(0, 2, 1) @ delta + A.permute(0, 2, 1) @ delta_v
-        pred_v = torch.cholesky_solve(b, torch.linalg.cholesky(A_augm))
+        pred_v = torch.cholesky_solve(b, torch.linalg.cholesky(A_augm)).to(f32)
         mask_pred, p2f = _SoftRender.apply(torch_ref.to_ndc(pred_v, cam, offset_z), fn, img_size)
         mask_loss = torch_ref.l1_loss(mask_pred, masks).mean()
         pred_proj = torch_ref.orthographic_proj_withz(pred_v, cam, 0.0)[..., :2]

@@ -58,8 +58,13 @@ def test_post_optimizer_vs_cpu_restatement(optimize_camera):
                       ).first_gradient(c["mean_v"], c["lbs"], c["L"], c["delta"], c["cam"], c["masks"], c["edts"], c["bds"],
                                        c["faces"], c["sel"])
     assert abs(float(g["loss"]) - ref["losses"][0]) <= 2e-4 * ref["losses"][0]
-    for k, gr in ref["grad0"].items():
+    # truth for the gradient: the same restatement with the handle solve in fp64 (the reference's fp32 batched Cholesky alone
+    # moves the gradient by ~2e-3: ref["grad0"] is checked at that level, the fp64 one at 1e-3)
+    ref64 = predictor_ref.post_optimize(d["mean_v"], d["lbs"], d["L"], d["delta"], d["cam"], d["masks"], d["edts"], d["bds"],
+                                        d["faces"], d["sel"][:1], d["S"], optimize_camera=optimize_camera, solve_dtype=torch.float64)
+    for k, gr in ref64["grad0"].items():
         assert util.rel_err(g[k].cpu().numpy(), gr.numpy()) < 1e-3, k
+        assert util.rel_err(g[k].cpu().numpy(), ref["grad0"][k].numpy()) < 5e-3, k
     assert ref["losses"][-1] < ref["losses"][0]                                  # the loop does optimise
     assert np.allclose(outs[True]["losses"].cpu().numpy(), outs[False]["losses"].cpu().numpy(), rtol=1e-4)
 

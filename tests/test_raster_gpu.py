@@ -427,7 +427,7 @@ def test_rasterize_of_and_tree_defaults():
 
 @pytest.mark.parametrize("with_edt,NBdiv", [(True, 1), (True, 4), (False, 2)])
 def test_fused_mask_losses_equal_the_two_pass_route(with_edt, NBdiv):
-    """acfm_raster_fwd_losses / acfm_raster_soft_bwd_losses (the mask-loss sums accumulated in the render's epilogue, their
+    """acfm_raster_fwd_train / acfm_raster_soft_bwd_train (the mask-loss sums accumulated in the render's epilogue, their
     backward formed inside the rasterizer backward) against the unfused route (render, then acfm_mask_sums_fwd / _bwd on the
     mask): same mask and fragments, sums within 1e-5 relative, vertex / camera gradients within 1e-4; an extra explicit
     gradient on the mask adds up with the one from the sums; the forward is bit-identical from call to call (ordered reductions)."""
