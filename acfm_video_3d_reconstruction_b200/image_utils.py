@@ -55,9 +55,13 @@ def compute_dt_both(mask, k=50):
     return _edt(mask, k, False, True, True)
 
 
-def compute_boundaries(masks):
+def compute_boundaries(masks, max_bd=None, return_counts=False):
     """(NB, max_bd, 3) float32 [x, y, valid] boundary points of each mask, padded to the longest list
-    (utils/image.py:122-146).  One host sync: the output length depends on the data."""
+    (utils/image.py:122-146).  max_bd=None: one host sync, the output length depends on the data (the reference's
+    behaviour).  max_bd=int: the caller's capacity — no host sync, so the call can be captured in a CUDA graph with the
+    rest of the step; lists longer than max_bd are truncated in raster-scan order (their tail is dropped) and shorter ones
+    padded with (-1, -1, 0) as usual.  return_counts=True also returns the (NB,) int32 device tensor of true list lengths,
+    which the caller can check against max_bd after the step."""
     m, _ = _batched(masks)
     NB, H, W = m.shape
     dev = m.device
@@ -67,9 +71,11 @@ def compute_boundaries(masks):
     with torch.cuda.device(dev):
         st = L.acfm_boundaries_count(_lib.ptr(m), NB, H, W, _lib.ptr(offs), _lib.ptr(tot), _lib.stream_of(m))
         _lib.check(st, "acfm_boundaries_count")
-        max_bd = int(tot.max()) if NB else 0
+        if max_bd is None:
+            max_bd = int(tot.max()) if NB else 0
+        max_bd = int(max_bd)
         out = torch.empty((NB, max_bd, 3), dtype=torch.float32, device=dev)
         st = L.acfm_boundaries_write(_lib.ptr(m), _lib.ptr(offs), _lib.ptr(tot), NB, H, W, max_bd, _lib.ptr(out), _lib.stream_of(m))
         _lib.check(st, "acfm_boundaries_write")
     _lib.count(3)
-    return out
+    return (out, tot) if return_counts else out

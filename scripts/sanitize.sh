@@ -12,7 +12,7 @@ mkdir -p gpurun_out
 rc=0
 for tool in memcheck racecheck initcheck synccheck; do
   compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
-    python -m pytest tests/test_raster_gpu.py -x -q -m gpu -k "$sel" > gpurun_out/sanitize_${tool}_${tag}.log 2>&1
+    python -m pytest tests/test_raster_gpu.py tests/test_deform_gpu.py -x -q -m gpu -k "$sel or handle" > gpurun_out/sanitize_${tool}_${tag}.log 2>&1
   r=$?
   echo "== $tool: exit $r"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/sanitize_${tool}_${tag}.log | tail -3
   [ $r -ne 0 ] && rc=$r

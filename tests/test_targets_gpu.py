@@ -45,3 +45,27 @@ def test_target_maps_256_vs_scipy():
     assert np.allclose(b.cpu().numpy(), np.stack([tr.compute_dt_barrier(x) for x in mn]).astype(np.float32), rtol=1e-6, atol=1e-30)
     assert np.array_equal(image_utils.compute_boundaries(m).cpu().numpy(), tr.compute_boundaries(mn))
     assert 0.03 < float(m.mean()) < 0.5
+
+
+def test_boundaries_with_capacity_is_capturable():
+    """compute_boundaries(max_bd=cap): no host sync — the call records into a CUDA graph; a larger cap pads with (-1,-1,0),
+    a smaller one keeps the first cap points of the raster scan; the true counts come back on the device."""
+    from acfm_video_3d_reconstruction_b200 import image_utils
+    g = util.golden("targets.npz")
+    m = torch.from_numpy(g["masks"]).cuda()
+    want = g["boundaries"]
+    nb, L = want.shape[0], want.shape[1]
+    image_utils.compute_boundaries(m, max_bd=L + 7)            # warm-up outside the capture
+    gr = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.cuda.graph(gr, stream=s):
+        big, cnt = image_utils.compute_boundaries(m, max_bd=L + 7, return_counts=True)
+        small = image_utils.compute_boundaries(m, max_bd=max(L - 5, 1))
+    gr.replay()
+    torch.cuda.synchronize()
+    big, small, cnt = big.cpu().numpy(), small.cpu().numpy(), cnt.cpu().numpy()
+    assert np.array_equal(big[:, :L], want)
+    assert np.array_equal(big[:, L:], np.broadcast_to(np.float32([-1, -1, 0]), (nb, 7, 3)))
+    assert np.array_equal(small, want[:, :small.shape[1]])
+    assert np.array_equal(cnt, (want[..., 2] > 0).sum(1))
