@@ -15,11 +15,12 @@ namespace {
 // fragments starting at a lane-dependent offset, so that neighbouring pixels (which see the same faces
 // at the same depth rank) touch different vertices at the same time.  Shared-memory FLOAT atomics are CAS spin
 // loops on sm_100 (ATOMS.CAST.SPIN) while 32-bit INTEGER adds are native fire-and-forget ATOMS.ADD, so the silhouette
-// path accumulates in fixed point: a per-CTA power-of-two scale is derived from the largest |grad_mask| of the
-// region (every contribution with |q - p| <= kRmax is then bounded by 2^24), and each contribution is split into a
-// signed high part (|.| <= 2^12) and a 12-bit low part added to two int32 accumulators — exact to 2^-24 of the bound and
+// path accumulates in fixed point: a per-CTA power-of-two scale is derived from the largest |grad_mask (1 - mask)| of the
+// region (every contribution with |q - p| <= kRmax is then bounded by 2^22), converted by one FFMA onto a magic constant (no
+// F2I: that is an XU-pipe instruction the atomics would wait for), and each contribution is split into a
+// signed high part (|.| <= 2^10) and a 12-bit low part added to two int32 accumulators — exact to 2^-22 of the bound and
 // independent of the order of the additions.  Headroom: the low plane takes 2^18 additions (4095 * 2^18 < 2^31), the high
-// plane 2^19; one CTA adds at most 1024 pixels x K <= 64 fragments = 2^16 contributions to one vertex component.  The rare contribution beyond the bound (a
+// plane 2^21; one CTA adds at most 1024 pixels x K <= 64 fragments = 2^16 contributions to one vertex component.  The rare contribution beyond the bound (a
 // face larger than kRmax on screen) goes straight to global memory as a float atomic.  Gradients reach HBM as one
 // atomicAdd per touched (CTA, vertex, component) instead of PyTorch3D's 4-9 global atomics per fragment.
 // ---------------------------------------------------------------------------------------------
@@ -48,67 +49,98 @@ struct BwdSmem {
   int off_verts, off_faces, off_acc, off_list, total;
   __host__ __device__ BwdSmem(int V, int F) {
     int o = 32;
-    off_verts = o; o += ((V * 12 + 16 + 15) / 16) * 16;
+    off_verts = o; o += ((V * 8 + 15) / 16) * 16;  // (x, y) per vertex
     off_faces = o; o += F * 8;
-    off_acc = o; o += ((V * 16 + 15) / 16) * 16;  // (V,2) x {high, low} int32 (fixed point) or (V,2) float
+    off_acc = o; o += V * 16;  // per vertex {x high, x low, y high, y low} int32 (fixed point) or (V,2) float
     off_list = o; o += kRegion * kRegion * 2;
     total = o;
   }
 };
 
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Squared distance from p to segment ab with the clamped parameter t and the foot point q (fast arithmetic: the backward
 // is held to 1e-3 relative, not to bit parity; only the CHOICE of the closest edge has to agree with the forward, and near a
-// tie either choice has the same gradient to that tolerance).
-__device__ __forceinline__ float seg_foot(float px, float py, float ax, float ay, float bx, float by, float& t, float& qx, float& qy) {
+// tie either choice has the same gradient to that tolerance).  dax, day = p - a.  Branch free: a degenerate edge (|ab|^2 = 0 or
+// denormal) gives t = 0 * inf = NaN or +-inf, which the clamp turns into 0 or 1 — q = a = b either way.
+__device__ __forceinline__ float seg_foot(float px, float py, float ax, float ay, float dax, float day, float bx, float by, float& t,
+                                          float& qx, float& qy) {
   const float bax = bx - ax, bay = by - ay;
-  const float l2 = bax * bax + bay * bay;
-  t = l2 > 0.0f ? __fdividef(bax * (px - ax) + bay * (py - ay), l2) : 0.0f;
+  const float l2 = fmaf(bax, bax, bay * bay);
+  t = fmaf(bax, dax, bay * day) * rcp_fast(l2);
   t = fminf(fmaxf(t, 0.0f), 1.0f);
   qx = fmaf(t, bax, ax); qy = fmaf(t, bay, ay);
   const float dx = qx - px, dy = qy - py;
-  return dx * dx + dy * dy;
+  return fmaf(dx, dx, dy * dy);
 }
 
-constexpr float kRmax = 0.25f;  // fixed-point bound on |q - p| (NDC): blur band 0.03, faces up to half a screen wide
+// fixed-point bound on |q - p| (NDC): the blur band is 0.03 wide and a pixel inside a face is at most the face's inradius from
+// its closest edge, so faces up to ~1/8 of the screen wide stay in range.  The bound sets the quantum of the accumulation
+// (bound / 2^22 per contribution): 1/16 with 22 bits resolves what 1/4 with 24 bits did.
+constexpr float kRmax = 0.0625f;
 
-// accumulation policy of one CTA: fixed point (silhouette path) or float CAS (general path)
+// accumulation policy of one CTA: fixed point (silhouette path) or float CAS (general path).  add_edge() takes the gradient
+// (gx, gy) of one fragment w.r.t. its foot point and splits it between the edge's vertices a, b by (1 - t, t).
+constexpr float kFxMagic = 12582912.0f;       // 1.5 * 2^23: float -> int by one FFMA (|value| <= 2^22), no F2I on the XU pipe
+constexpr int kFxMagicBits = 0x4B400000;
+// Layout: (V,2) high parts, then (V,2) low parts.  (Measured worse at C2: {x high, x low, y high, y low} per vertex, one base
+// address per vertex — 0.57 -> 0.62 ms, twice the bank conflicts between vertices; giving a warp 32 pixels that lie far apart
+// in the region instead of 32 neighbours, so that lanes rarely meet at one vertex — 0.57 -> 0.71 ms: neighbours reading the
+// same face and vertex words is what keeps the shared loads cheap.)
 struct AccFixed {
-  int* hi; int* lo; float scale; float* gout;  // gout: global fallback for out-of-range contributions
-  __device__ __forceinline__ void add(int i, float c, bool in_range) const {
+  int* acc; int plane; float scale; float* gout;  // gout: global fallback for out-of-range contributions
+  __device__ __forceinline__ void add1(int* a, float c) const {
+    const int v = __float_as_int(fmaf(c, scale, kFxMagic)) - kFxMagicBits;  // round to nearest even, like F2I.RN
+    atomicAdd(a, v >> 12);
+    atomicAdd(a + plane, v & 4095);
+  }
+  __device__ __forceinline__ void add_edge(int ia, int ib, float t, float gx, float gy, bool in_range) const {
+    const float s = 1.0f - t;
     if (in_range) {
-      const int v = __float2int_rn(c * scale);
-      atomicAdd(hi + i, v >> 12);
-      atomicAdd(lo + i, v & 4095);
+      int* a = acc + ia * 2;
+      int* b = acc + ib * 2;
+      add1(a, s * gx); add1(a + 1, s * gy); add1(b, t * gx); add1(b + 1, t * gy);
     } else {
-      atomicAdd(gout + (i >> 1) * 3 + (i & 1), c);
+      atomicAdd(gout + ia * 3, s * gx); atomicAdd(gout + ia * 3 + 1, s * gy);
+      atomicAdd(gout + ib * 3, t * gx); atomicAdd(gout + ib * 3 + 1, t * gy);
     }
   }
 };
 struct AccFloat {
   float* acc;
-  __device__ __forceinline__ void add(int i, float c, bool) const { atomicAdd(acc + i, c); }
+  __device__ __forceinline__ void add_edge(int ia, int ib, float t, float gx, float gy, bool) const {
+    const float s = 1.0f - t;
+    atomicAdd(acc + ia * 2, s * gx); atomicAdd(acc + ia * 2 + 1, s * gy);
+    atomicAdd(acc + ib * 2, t * gx); atomicAdd(acc + ib * 2 + 1, t * gy);
+  }
 };
 
 // gradient of one fragment's squared distance w.r.t. the two vertices of its closest edge (PointLineDistanceBackward,
-// SURVEY.md §9.6), accumulated into the CTA's (V,2) accumulator
+// SURVEY.md §9.6), accumulated into the CTA's per-vertex accumulator
 template <typename Acc>
-__device__ __forceinline__ void frag_grad(float px, float py, float x0, float y0, float x1, float y1, float x2, float y2, float g,
-                                          int i0, int i1, int i2, const Acc& acc) {
+__device__ __forceinline__ void frag_grad(float px, float py, float2 v0, float2 v1, float2 v2, float g, int i0, int i1, int i2, const Acc& acc) {
   float t01, t02, t12, qx01, qy01, qx02, qy02, qx12, qy12;
-  const float d01 = seg_foot(px, py, x0, y0, x1, y1, t01, qx01, qy01);
-  const float d02 = seg_foot(px, py, x0, y0, x2, y2, t02, qx02, qy02);
-  const float d12 = seg_foot(px, py, x1, y1, x2, y2, t12, qx12, qy12);
-  float t, qx, qy, dm;
-  int ia, ib;
-  if (d01 <= d02 && d01 <= d12) { t = t01; qx = qx01; qy = qy01; ia = i0; ib = i1; dm = d01; }       // same order as the forward's min
-  else if (d02 <= d12) { t = t02; qx = qx02; qy = qy02; ia = i0; ib = i2; dm = d02; }
-  else { t = t12; qx = qx12; qy = qy12; ia = i1; ib = i2; dm = d12; }
-  const bool in_range = dm <= kRmax * kRmax;
-  const float gx = g * 2.0f * (qx - px), gy = g * 2.0f * (qy - py);
-  acc.add(ia * 2, (1.0f - t) * gx, in_range);
-  acc.add(ia * 2 + 1, (1.0f - t) * gy, in_range);
-  acc.add(ib * 2, t * gx, in_range);
-  acc.add(ib * 2 + 1, t * gy, in_range);
+  const float d0x = px - v0.x, d0y = py - v0.y, d1x = px - v1.x, d1y = py - v1.y;
+  const float d01 = seg_foot(px, py, v0.x, v0.y, d0x, d0y, v1.x, v1.y, t01, qx01, qy01);
+  const float d02 = seg_foot(px, py, v0.x, v0.y, d0x, d0y, v2.x, v2.y, t02, qx02, qy02);
+  const float d12 = seg_foot(px, py, v1.x, v1.y, d1x, d1y, v2.x, v2.y, t12, qx12, qy12);
+  // same order as the forward's min: 01, then 02, then 12
+  const bool c01 = d01 <= d02 && d01 <= d12, c02 = d02 <= d12;
+  const float t = c01 ? t01 : (c02 ? t02 : t12);
+  const float qx = c01 ? qx01 : (c02 ? qx02 : qx12), qy = c01 ? qy01 : (c02 ? qy02 : qy12);
+  const float dm = c01 ? d01 : (c02 ? d02 : d12);
+  const int ia = (c01 || c02) ? i0 : i1, ib = c01 ? i1 : i2;
+  const float g2 = g + g;
+  acc.add_edge(ia, ib, t, g2 * (qx - px), g2 * (qy - py), dm <= kRmax * kRmax);
 }
 
 // d loss / d mask at one pixel: the caller's grad_mask and / or the backward of the fused per-render sums
@@ -133,13 +165,12 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   constexpr int NT = 128, NWARPS = 4;
   extern __shared__ __align__(16) unsigned char smem[];
   const BwdSmem L(p.V, p.F);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   int* nactive = reinterpret_cast<int*>(smem + 8);
   int* next_chunk = reinterpret_cast<int*>(smem + 12);
   ushort4* sfaces = reinterpret_cast<ushort4*>(smem + L.off_faces);
   float* accf = reinterpret_cast<float*>(smem + L.off_acc);
-  int* acc_hi = reinterpret_cast<int*>(smem + L.off_acc);
-  int* acc_lo = acc_hi + p.V * 2;
+  int4* accq = reinterpret_cast<int4*>(smem + L.off_acc);
+  float2* sxy = reinterpret_cast<float2*>(smem + L.off_verts);
   unsigned* gmax_bits = reinterpret_cast<unsigned*>(smem + 16);
   unsigned short* alist = reinterpret_cast<unsigned short*>(smem + L.off_list);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -176,7 +207,7 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
       const long long pix = ((long long)n * p.H + y) * p.W + x;
       if (FROM_MASK) {
         const float mv = p.mask[pix];
-        gabs = mv != 0.0f ? fabsf(upstream_grad(p, n, pix, x, y, mv)) : 0.0f;
+        gabs = mv != 0.0f ? fabsf(upstream_grad(p, n, pix, x, y, mv) * (1.0f - mv)) : 0.0f;  // |ga| sigma of the loop below
         act = (mv != 0.0f) && (gabs != 0.0f) && (gabs <= 3.0e38f);  // NaN / inf upstream gradients are dropped
         if (!act) gabs = 0.0f;
       } else {
@@ -199,29 +230,32 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   const int na = *nactive;
   if (na == 0) return;
 
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   const long long fbase = (long long)n * p.faces_stride;
   for (int f = tid; f < p.F; f += NT) {
     const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)f * 3;
     sfaces[f] = make_ushort4((unsigned short)fp[0], (unsigned short)fp[1], (unsigned short)fp[2], 0);
   }
-  for (int i = tid; i < p.V * 4; i += NT) acc_hi[i] = 0;  // both int32 planes; as floats, 0.0f twice over
+  const float* gv3 = p.ndc + (size_t)n * p.V * 3;
+  for (int i = tid; i < p.V; i += NT) {
+    accq[i] = make_int4(0, 0, 0, 0);  // (as floats: 0.0f four times over)
+    sxy[i] = make_float2(gv3[i * 3], gv3[i * 3 + 1]);  // x, y only: one 8-byte shared load per vertex in the fragment loop
+  }
   __syncthreads();
-  const float* sv = stage_bulk_1d(smem + L.off_verts, p.ndc + (size_t)n * p.V * 3, (uint32_t)p.V * 12u, bar, 0);
 
   // ---- 2. one active pixel per lane, 32 at a time, chunks pulled dynamically --------------------------
   const float inv_sigma = 1.0f / p.sigma;
+  const float sig_l2e = inv_sigma * 1.4426950408889634f;  // prob = 1 / (1 + 2^(d log2(e) / sigma))
   const float inv_w = 1.0f / (float)p.W, inv_h = 1.0f / (float)p.H;
   float* gout = p.grad_ndc + (size_t)n * p.V * 3;
-  // |contribution| <= |grad_mask| / sigma * 2 |q - p| (alpha, prob, t <= 1)  =>  bound = gmax / sigma * 2 kRmax, rounded up
+  // |contribution| <= |grad_mask (1 - mask)| / sigma * 2 |q - p| (prob, t <= 1)  =>  bound = gmax / sigma * 2 kRmax, rounded up
   // to a power of two; scale maps the bound to 2^24
   float fx_scale = 1.0f;
   if (FROM_MASK) {
     int e;
     frexpf(__uint_as_float(*gmax_bits) * inv_sigma * (2.0f * kRmax), &e);  // bound < 2^e (gmax is finite and > 0 here)
-    fx_scale = ldexpf(1.0f, 24 - max(e, -100));  // (clamped: a vanishing bound must not push the scale to infinity)
+    fx_scale = ldexpf(1.0f, 22 - max(e, -100));  // (clamped: a vanishing bound must not push the scale to infinity)
   }
-  const AccFixed accx{acc_hi, acc_lo, fx_scale, gout};
+  const AccFixed accx{reinterpret_cast<int*>(accq), p.V * 2, fx_scale, gout};
   const AccFloat accl{accf};
   const int nchunks = (na + 31) / 32;
   const bool vec = (K & 3) == 0 && (((uintptr_t)p.p2f | (uintptr_t)p.dists | (FROM_MASK ? 0 : (uintptr_t)p.grad_dists)) & 15u) == 0;
@@ -240,6 +274,20 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
     const long long* pf = p.p2f + pix * K;
     const float* pd = p.dists + pix * K;
     const long long nF = (long long)n * p.F;
+    // fragments in groups of four (16-byte loads); the first group's loads are issued before the upstream gradient is formed
+    // and every later group's while the one before it is processed: the kernel is bound by the latency of these loads and of
+    // the shared atomics, so one group is always in flight.  Lanes start at different groups so that neighbouring pixels,
+    // which see the same faces at the same depth rank, touch different vertices at the same time.
+    const int groups = K >> 2;
+    int g = vec ? lane % groups : 0;
+    longlong2 fa = make_longlong2(-1, -1), fb = fa;
+    float4 dd = make_float4(0.f, 0.f, 0.f, 0.f), gg = dd;
+    if (vec) {
+      fa = *reinterpret_cast<const longlong2*>(pf + 4 * g);
+      fb = *reinterpret_cast<const longlong2*>(pf + 4 * g + 2);
+      dd = *reinterpret_cast<const float4*>(pd + 4 * g);
+      if (!FROM_MASK) gg = *reinterpret_cast<const float4*>(p.grad_dists + pix * K + 4 * g);
+    }
     // d mask / d dist_k = -(prob_k / sigma) * prod_j (1 - prob_j)   (SURVEY.md §9.5); the product is 1 - mask, which the
     // forward already formed (its rounding only matters where the product, hence the gradient, is < 1e-7 of the largest)
     float ga = 1.0f;
@@ -249,37 +297,31 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
       if (ga == 0.0f) continue;
     }
     if (vec) {
-      // fragments in groups of four (16-byte loads, all issued before use); lanes start at different groups so that
-      // neighbouring pixels, which see the same faces at the same depth rank, touch different vertices at the same time.
       // (Measured without gain: combining the lanes that hit the same vertex with __match_any_sync + __reduce_add_sync before
       // the shared atomics — 0.63 -> 1.98 ms at C2, the match is far slower than the conflicts it removes; saving the closest
       // edge per fragment in the forward so that one foot point is computed instead of three — 0.64 -> 0.63 ms for +0.07 ms
       // of forward: the kernel waits on fragment loads and shared atomics, not on arithmetic.)
-      const int groups = K >> 2;
-      int g = lane % groups;
       for (int s = 0; s < groups; ++s) {
-        const longlong2 fa = *reinterpret_cast<const longlong2*>(pf + 4 * g);
-        const longlong2 fb = *reinterpret_cast<const longlong2*>(pf + 4 * g + 2);
-        const float4 dd = *reinterpret_cast<const float4*>(pd + 4 * g);
-        float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!FROM_MASK) gg = *reinterpret_cast<const float4*>(p.grad_dists + pix * K + 4 * g);
         const long long fid[4] = {fa.x, fa.y, fb.x, fb.y};
         const float dv[4] = {dd.x, dd.y, dd.z, dd.w};
         const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
         g = (g + 1 == groups) ? 0 : g + 1;
+        if (s + 1 < groups) {  // next group: in flight during this one's arithmetic
+          fa = *reinterpret_cast<const longlong2*>(pf + 4 * g);
+          fb = *reinterpret_cast<const longlong2*>(pf + 4 * g + 2);
+          dd = *reinterpret_cast<const float4*>(pd + 4 * g);
+          if (!FROM_MASK) gg = *reinterpret_cast<const float4*>(p.grad_dists + pix * K + 4 * g);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (fid[e] < 0) break;  // lists are front-packed
           const float d = dv[e];
-          float gd = FROM_MASK ? ga * __fdividef(1.0f, 1.0f + __expf(d * inv_sigma)) : gv[e];
+          float gd = FROM_MASK ? ga * rcp_fast(1.0f + ex2_fast(d * sig_l2e)) : gv[e];
           if (gd == 0.0f) continue;
           if (signbit(d)) gd = -gd;  // dist = inside ? -|d| : |d|
-          const ushort4 iv = sfaces[(int)(fid[e] - nF)];
-          if (FROM_MASK) {
-            frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accx);
-          } else {
-            frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accl);
-          }
+          const ushort4 iv = sfaces[(int)((unsigned)fid[e] - (unsigned)nF)];  // (0 <= fid - nF < F: the low words suffice)
+          if (FROM_MASK) frag_grad(xf, yf, sxy[iv.x], sxy[iv.y], sxy[iv.z], gd, iv.x, iv.y, iv.z, accx);
+          else frag_grad(xf, yf, sxy[iv.x], sxy[iv.y], sxy[iv.z], gd, iv.x, iv.y, iv.z, accl);
         }
       }
     } else {
@@ -290,20 +332,21 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
       for (int s = 0; s < cnt; ++s) {
         const float d = pd[k];
         const int f = (int)(pf[k] - nF);
-        float gd = FROM_MASK ? ga * __fdividef(1.0f, 1.0f + __expf(d * inv_sigma)) : p.grad_dists[pix * K + k];
+        float gd = FROM_MASK ? ga * rcp_fast(1.0f + ex2_fast(d * sig_l2e)) : p.grad_dists[pix * K + k];
         k = (k + 1 == cnt) ? 0 : k + 1;
         if (gd == 0.0f) continue;
         if (signbit(d)) gd = -gd;
         const ushort4 iv = sfaces[f];
-        if (FROM_MASK) frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accx);
-        else frag_grad(xf, yf, sv[iv.x * 3], sv[iv.x * 3 + 1], sv[iv.y * 3], sv[iv.y * 3 + 1], sv[iv.z * 3], sv[iv.z * 3 + 1], gd, iv.x, iv.y, iv.z, accl);
+        if (FROM_MASK) frag_grad(xf, yf, sxy[iv.x], sxy[iv.y], sxy[iv.z], gd, iv.x, iv.y, iv.z, accx);
+        else frag_grad(xf, yf, sxy[iv.x], sxy[iv.y], sxy[iv.z], gd, iv.x, iv.y, iv.z, accl);
       }
     }
   }
   __syncthreads();
   const float inv_scale = 1.0f / fx_scale;
   for (int i = tid; i < p.V * 2; i += NT) {
-    const float a = FROM_MASK ? ((float)acc_hi[i] * 4096.0f + (float)acc_lo[i]) * inv_scale : accf[i];
+    const int* q = reinterpret_cast<const int*>(accq) + i;  // component i & 1 of vertex i >> 1
+    const float a = FROM_MASK ? ((float)q[0] * 4096.0f + (float)q[p.V * 2]) * inv_scale : accf[i];
     if (a != 0.0f) atomicAdd(gout + (i >> 1) * 3 + (i & 1), a);
   }
 }
