@@ -19,6 +19,7 @@ SIGNATURES = {
     "acfm_version": [],
     "acfm_last_error_string": [],
     "acfm_set_raster_epsilon": [_c_f],
+    "acfm_set_raster_bwd_headroom_bits": [_c_int],
     "acfm_get_raster_epsilon": [],
     "acfm_project_fwd": [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_f, _c_f, _c_vp, _c_vp],
     "acfm_project_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp, _c_vp],

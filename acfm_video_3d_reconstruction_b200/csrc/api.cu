@@ -9,6 +9,7 @@
 namespace {
 thread_local char g_err[512] = "";
 std::atomic<float> g_raster_eps{ACFM_K_EPS_DEFAULT};
+std::atomic<int> g_bwd_headroom_bits{30};
 }
 
 float acfm_raster_epsilon() { return g_raster_eps.load(std::memory_order_relaxed); }
@@ -20,6 +21,14 @@ extern "C" int acfm_set_raster_epsilon(float eps) {
 }
 
 extern "C" float acfm_get_raster_epsilon(void) { return acfm_raster_epsilon(); }
+
+int acfm_raster_bwd_headroom_bits() { return g_bwd_headroom_bits.load(std::memory_order_relaxed); }
+
+extern "C" int acfm_set_raster_bwd_headroom_bits(int bits) {
+  ACFM_REQUIRE(bits >= 16 && bits <= 30, ACFM_ERR_BAD_ARG, "acfm_set_raster_bwd_headroom_bits: bits must be in 16..30");
+  g_bwd_headroom_bits.store(bits, std::memory_order_relaxed);
+  return ACFM_OK;
+}
 
 void acfm_set_error(const char* fmt, ...) {
   va_list ap;

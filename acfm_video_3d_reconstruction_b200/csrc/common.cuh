@@ -72,6 +72,7 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 // neighbours is sensitive to it (tests/test_oracle_variants.py) and the value cannot be checked against the upstream source here.
 #define ACFM_K_EPS_DEFAULT 1e-8f
 float acfm_raster_epsilon();  // host: the current setting (api.cu)
+int acfm_raster_bwd_headroom_bits();  // host: acfm_set_raster_bwd_headroom_bits (api.cu; raster_bwd.cu)
 
 // PixToNdc: -1 + (2 i + 1) / S
 __device__ __forceinline__ float pix_to_ndc(int i, int S) {

@@ -17,10 +17,15 @@ namespace {
 // loops on sm_100 (ATOMS.CAST.SPIN) while 32-bit INTEGER adds are native fire-and-forget ATOMS.ADD, so the silhouette
 // path accumulates in fixed point: a per-CTA power-of-two scale is derived from the largest |grad_mask (1 - mask)| of the
 // region (every contribution with |q - p| <= kRmax is then bounded by 2^22), converted by one FFMA onto a magic constant (no
-// F2I: that is an XU-pipe instruction the atomics would wait for), and each contribution is split into a
-// signed high part (|.| <= 2^10) and a 12-bit low part added to two int32 accumulators — exact to 2^-22 of the bound and
-// independent of the order of the additions.  Headroom: the low plane takes 2^18 additions (4095 * 2^18 < 2^31), the high
-// plane 2^21; one CTA adds at most 1024 pixels x K <= 64 fragments = 2^16 contributions to one vertex component.  The rare contribution beyond the bound (a
+// F2I: that is an XU-pipe instruction the atomics would wait for) and added to ONE int32 per vertex component — the shared
+// atomic unit retires about four lanes per cycle whatever the addresses (ncu: 5.2 wavefronts per ATOMS at 19 active lanes,
+// with or without lanes meeting at a vertex), so the number of atomics is what the kernel pays for: four per fragment, not
+// the eight of a high / low pair of planes.  An int32 cannot hold the worst case (2^16 contributions of 2^22), so the
+// headroom is VERIFIED instead of assumed: every lane sums the magnitudes it adds, the CTA checks sum |contribution| * scale
+// < 2^30 — a bound on every accumulator, wrap-around included: two's-complement sums are exact whenever the true result
+// fits — and in the rare region that fails (thousands of large contributions) clears the accumulators and runs the region
+// again with the scale that passes.  Exact to 2^-22 of the bound (2^-k less after a retry) and independent of the order of
+// the additions.  The rare contribution beyond the bound (a
 // face larger than kRmax on screen) goes straight to global memory as a float atomic.  Gradients reach HBM as one
 // atomicAdd per touched (CTA, vertex, component) instead of PyTorch3D's 4-9 global atomics per fragment.
 // ---------------------------------------------------------------------------------------------
@@ -39,6 +44,7 @@ struct BwdParams {
   const float* loss_target; // (NB,H,W)
   const float* loss_edt;    // (NB,H,W) or NULL
   int NB;
+  float headroom;           // fixed-point accumulators: largest admissible sum of scaled magnitudes (2^30)
   const float* grad_dists;  // FROM_MASK == false: upstream gradient per fragment (N,H,W,K)
   float* grad_ndc;
   int regions_x, regions_y;
@@ -51,7 +57,7 @@ struct BwdSmem {
     int o = 32;
     off_verts = o; o += ((V * 8 + 15) / 16) * 16;  // (x, y) per vertex
     off_faces = o; o += F * 8;
-    off_acc = o; o += V * 16;  // per vertex {x high, x low, y high, y low} int32 (fixed point) or (V,2) float
+    off_acc = o; o += ((V * 8 + 15) / 16) * 16;  // (V,2) int32 (fixed point) or float
     off_list = o; o += kRegion * kRegion * 2;
     total = o;
   }
@@ -92,24 +98,24 @@ constexpr float kRmax = 0.0625f;
 // (gx, gy) of one fragment w.r.t. its foot point and splits it between the edge's vertices a, b by (1 - t, t).
 constexpr float kFxMagic = 12582912.0f;       // 1.5 * 2^23: float -> int by one FFMA (|value| <= 2^22), no F2I on the XU pipe
 constexpr int kFxMagicBits = 0x4B400000;
-// Layout: (V,2) high parts, then (V,2) low parts.  (Measured worse at C2: {x high, x low, y high, y low} per vertex, one base
-// address per vertex — 0.57 -> 0.62 ms, twice the bank conflicts between vertices; giving a warp 32 pixels that lie far apart
-// in the region instead of 32 neighbours, so that lanes rarely meet at one vertex — 0.57 -> 0.71 ms: neighbours reading the
-// same face and vertex words is what keeps the shared loads cheap.)
+// (Measured worse at C2: a high and a low int32 plane per component — eight atomics per fragment, headroom by construction —
+// 0.58 ms against 0.42 ms; {x, y} interleaved with one base address per vertex; giving a warp 32 pixels that
+// lie far apart in the region instead of 32 neighbours — 0.57 -> 0.71 ms: neighbours reading the same face and vertex words is
+// what keeps the shared loads cheap; starting every lane at its own depth rank — no change.)
 struct AccFixed {
-  int* acc; int plane; float scale; float* gout;  // gout: global fallback for out-of-range contributions
+  int* acc; float scale; float* gout; bool far_ok;  // gout: global fallback for out-of-range contributions (first pass only)
+  float sx = 0.0f, sy = 0.0f;                       // magnitudes this lane has added (headroom check)
   __device__ __forceinline__ void add1(int* a, float c) const {
-    const int v = __float_as_int(fmaf(c, scale, kFxMagic)) - kFxMagicBits;  // round to nearest even, like F2I.RN
-    atomicAdd(a, v >> 12);
-    atomicAdd(a + plane, v & 4095);
+    atomicAdd(a, __float_as_int(fmaf(c, scale, kFxMagic)) - kFxMagicBits);  // round to nearest even, like F2I.RN
   }
-  __device__ __forceinline__ void add_edge(int ia, int ib, float t, float gx, float gy, bool in_range) const {
+  __device__ __forceinline__ void add_edge(int ia, int ib, float t, float gx, float gy, bool in_range) {
     const float s = 1.0f - t;
     if (in_range) {
       int* a = acc + ia * 2;
       int* b = acc + ib * 2;
       add1(a, s * gx); add1(a + 1, s * gy); add1(b, t * gx); add1(b + 1, t * gy);
-    } else {
+      sx += fabsf(gx); sy += fabsf(gy);
+    } else if (far_ok) {
       atomicAdd(gout + ia * 3, s * gx); atomicAdd(gout + ia * 3 + 1, s * gy);
       atomicAdd(gout + ib * 3, t * gx); atomicAdd(gout + ib * 3 + 1, t * gy);
     }
@@ -117,7 +123,7 @@ struct AccFixed {
 };
 struct AccFloat {
   float* acc;
-  __device__ __forceinline__ void add_edge(int ia, int ib, float t, float gx, float gy, bool) const {
+  __device__ __forceinline__ void add_edge(int ia, int ib, float t, float gx, float gy, bool) {
     const float s = 1.0f - t;
     atomicAdd(acc + ia * 2, s * gx); atomicAdd(acc + ia * 2 + 1, s * gy);
     atomicAdd(acc + ib * 2, t * gx); atomicAdd(acc + ib * 2 + 1, t * gy);
@@ -127,7 +133,7 @@ struct AccFloat {
 // gradient of one fragment's squared distance w.r.t. the two vertices of its closest edge (PointLineDistanceBackward,
 // SURVEY.md §9.6), accumulated into the CTA's per-vertex accumulator
 template <typename Acc>
-__device__ __forceinline__ void frag_grad(float px, float py, float2 v0, float2 v1, float2 v2, float g, int i0, int i1, int i2, const Acc& acc) {
+__device__ __forceinline__ void frag_grad(float px, float py, float2 v0, float2 v1, float2 v2, float g, int i0, int i1, int i2, Acc& acc) {
   float t01, t02, t12, qx01, qy01, qx02, qy02, qx12, qy12;
   const float d0x = px - v0.x, d0y = py - v0.y, d1x = px - v1.x, d1y = py - v1.y;
   const float d01 = seg_foot(px, py, v0.x, v0.y, d0x, d0y, v1.x, v1.y, t01, qx01, qy01);
@@ -160,6 +166,8 @@ __device__ __forceinline__ float upstream_grad(const BwdParams& p, int n, long l
 
 // FROM_MASK: the upstream gradient is d loss / d mask and the blend backward (§9.5) is fused in;
 // otherwise it is d loss / d dists per fragment (texture branch, general rasterize_meshes backward on dists).
+// (71 registers, 22.6 KB of shared memory at the reference's templates: 7 CTAs per SM.  Capped at 63 registers for 8: no change;
+// at 56 for 9: 0.42 -> 0.50 ms at C2.)
 template <typename IdxT, bool FROM_MASK>
 __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p) {
   constexpr int NT = 128, NWARPS = 4;
@@ -169,7 +177,8 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   int* next_chunk = reinterpret_cast<int*>(smem + 12);
   ushort4* sfaces = reinterpret_cast<ushort4*>(smem + L.off_faces);
   float* accf = reinterpret_cast<float*>(smem + L.off_acc);
-  int4* accq = reinterpret_cast<int4*>(smem + L.off_acc);
+  int2* acci = reinterpret_cast<int2*>(smem + L.off_acc);
+  float* ssum = reinterpret_cast<float*>(smem + 20);  // [2]: magnitudes added in x, in y (headroom check)
   float2* sxy = reinterpret_cast<float2*>(smem + L.off_verts);
   unsigned* gmax_bits = reinterpret_cast<unsigned*>(smem + 16);
   unsigned short* alist = reinterpret_cast<unsigned short*>(smem + L.off_list);
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   const int px0 = (rg % p.regions_x) * kRegion, py0 = (rg / p.regions_x) * kRegion;
   const int K = p.K;
 
-  if (tid == 0) { *nactive = 0; *next_chunk = 0; *gmax_bits = 0u; }
+  if (tid == 0) { *nactive = 0; *next_chunk = 0; *gmax_bits = 0u; ssum[0] = 0.0f; ssum[1] = 0.0f; }
   __syncthreads();
   // ---- 1. compact the region's active pixels (coalesced reads of mask / grad_mask) -------------------
   for (int i0 = 0; i0 < kRegion * kRegion; i0 += NT) {
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   }
   const float* gv3 = p.ndc + (size_t)n * p.V * 3;
   for (int i = tid; i < p.V; i += NT) {
-    accq[i] = make_int4(0, 0, 0, 0);  // (as floats: 0.0f four times over)
+    acci[i] = make_int2(0, 0);  // (as floats: 0.0f twice over)
     sxy[i] = make_float2(gv3[i * 3], gv3[i * 3 + 1]);  // x, y only: one 8-byte shared load per vertex in the fragment loop
   }
   __syncthreads();
@@ -248,17 +257,19 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   const float inv_w = 1.0f / (float)p.W, inv_h = 1.0f / (float)p.H;
   float* gout = p.grad_ndc + (size_t)n * p.V * 3;
   // |contribution| <= |grad_mask (1 - mask)| / sigma * 2 |q - p| (prob, t <= 1)  =>  bound = gmax / sigma * 2 kRmax, rounded up
-  // to a power of two; scale maps the bound to 2^24
+  // to a power of two; scale maps the bound to 2^22
   float fx_scale = 1.0f;
   if (FROM_MASK) {
     int e;
     frexpf(__uint_as_float(*gmax_bits) * inv_sigma * (2.0f * kRmax), &e);  // bound < 2^e (gmax is finite and > 0 here)
     fx_scale = ldexpf(1.0f, 22 - max(e, -100));  // (clamped: a vanishing bound must not push the scale to infinity)
   }
-  const AccFixed accx{reinterpret_cast<int*>(accq), p.V * 2, fx_scale, gout};
-  const AccFloat accl{accf};
+  AccFixed accx{reinterpret_cast<int*>(acci), fx_scale, gout, true};
+  AccFloat accl{accf};
   const int nchunks = (na + 31) / 32;
   const bool vec = (K & 3) == 0 && (((uintptr_t)p.p2f | (uintptr_t)p.dists | (FROM_MASK ? 0 : (uintptr_t)p.grad_dists)) & 15u) == 0;
+  int passes = 1;
+pass_again:
   while (true) {
     int c = 0;
     if (lane == 0) c = atomicAdd(next_chunk, 1);
@@ -342,11 +353,31 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
       }
     }
   }
+  if (FROM_MASK) {
+    // headroom check: sum over the region of |gx| (|gy|) bounds the magnitude of every x (y) accumulator's true value
+    float sx = accx.sx, sy = accx.sy;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    if (lane == 0) { atomicAdd(&ssum[0], sx); atomicAdd(&ssum[1], sy); }
+  }
   __syncthreads();
-  const float inv_scale = 1.0f / fx_scale;
+  if (FROM_MASK) {
+    const float top = fmaxf(ssum[0], ssum[1]) * accx.scale;  // (+ half a unit of rounding per addition: far inside the 2x margin)
+    if (top >= p.headroom && top <= 3.0e38f && ++passes <= 4) {  // (never for NaN / inf: garbage in, garbage out, but no loop)
+      // run the region again with a scale that passes (the out-of-range contributions went to global memory already)
+      int e;
+      frexpf(top / p.headroom, &e);  // top / headroom < 2^e, e >= 1
+      __syncthreads();                            // everyone has read ssum
+      for (int i = tid; i < p.V; i += NT) acci[i] = make_int2(0, 0);
+      if (tid == 0) { *next_chunk = 0; ssum[0] = 0.0f; ssum[1] = 0.0f; }
+      accx.scale = ldexpf(accx.scale, -e); accx.far_ok = false; accx.sx = 0.0f; accx.sy = 0.0f;
+      __syncthreads();
+      goto pass_again;
+    }
+  }
+  const float inv_scale = 1.0f / accx.scale;
   for (int i = tid; i < p.V * 2; i += NT) {
-    const int* q = reinterpret_cast<const int*>(accq) + i;  // component i & 1 of vertex i >> 1
-    const float a = FROM_MASK ? ((float)q[0] * 4096.0f + (float)q[p.V * 2]) * inv_scale : accf[i];
+    const float a = FROM_MASK ? (float)reinterpret_cast<const int*>(acci)[i] * inv_scale : accf[i];
     if (a != 0.0f) atomicAdd(gout + (i >> 1) * 3 + (i & 1), a);
   }
 }
@@ -374,6 +405,7 @@ int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* fa
   p.N = N; p.V = V; p.F = F; p.H = H; p.W = W; p.K = K; p.sigma = from_mask ? sigma : 1.0f;
   p.p2f = (const long long*)pix_to_face; p.dists = dists; p.mask = mask; p.grad_mask = grad_mask; p.grad_dists = grad_dists;
   p.grad_ndc = grad_ndc;
+  p.headroom = ldexpf(1.0f, acfm_raster_bwd_headroom_bits());
   p.grad_sums = grad_sums; p.loss_target = loss_target; p.loss_edt = loss_edt; p.NB = NB > 0 ? NB : 1;
   p.work = (const int*)work;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;

@@ -38,6 +38,11 @@ const char* acfm_last_error_string(void);
 int acfm_set_raster_epsilon(float eps);
 float acfm_get_raster_epsilon(void);
 
+/* Test hook of the backward rasterizer's fixed-point accumulation (raster_bwd.cu): a region whose summed gradient magnitudes,
+ * scaled, reach 2^bits is accumulated a second time with a smaller scale.  Default 30 (the int32 accumulators then cannot
+ * wrap); tests lower it (16..30) to drive ordinary inputs through the second pass.  Process-wide. */
+int acfm_set_raster_bwd_headroom_bits(int bits);
+
 /* ---------------------------------------------------------------------------------------------
  * Projection.  Replaces geom_utils.orthographic_proj_withz / orthographic_proj / quat_rotate /
  * hamilton_product (multiframe/nnutils/geom_utils.py:48-153) and the view set-up of

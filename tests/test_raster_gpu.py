@@ -160,6 +160,40 @@ def test_edge_cases():
     _assert_fragments_equal(frc, refc)
 
 
+@pytest.mark.parametrize("upstream", ["ones", "normal"])
+def test_backward_second_pass_of_the_fixed_point_accumulation(upstream):
+    """The backward adds every contribution to ONE int32 per vertex component and verifies the headroom afterwards: a region
+    whose summed magnitudes reach 2^bits is accumulated again with a smaller scale.  With bits lowered from 30 to 20 nearly
+    every region of an ordinary render takes the second pass: same gradient (to the coarser quantum), still the oracle's."""
+    from acfm_video_3d_reconstruction_b200 import _lib
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    v, f = util.template("bird")
+    N, S = 3, 128
+    X, cam = util.synth_verts(v, N, seed=61), util.synth_cams(N, seed=62)
+    faces = np.repeat(f[None], N, 0)
+    ref = orc.neural_renderer_mask(X, faces, cam, img_size=S, offset_z=5.0)
+    gm = np.ones((N, S, S), np.float32) if upstream == "ones" else np.random.default_rng(3).standard_normal((N, S, S)).astype(np.float32)
+    g_ref = orc.neural_renderer_mask_backward(ref, faces, gm)
+    ndc0 = torch.from_numpy(ref["ndc"]).cuda()
+
+    def grad():
+        x = ndc0.clone().requires_grad_(True)
+        m, _, _, _ = F_.soft_silhouette(x, torch.from_numpy(faces).cuda(), S)
+        return torch.autograd.grad((m * torch.from_numpy(gm).cuda()).sum(), x)[0].cpu().numpy()
+
+    g30 = grad()
+    assert util.rel_err(g30, g_ref) < 1e-3
+    try:
+        _lib.check(_lib.lib().acfm_set_raster_bwd_headroom_bits(20), "acfm_set_raster_bwd_headroom_bits")
+        g24 = grad()
+    finally:
+        _lib.check(_lib.lib().acfm_set_raster_bwd_headroom_bits(30), "acfm_set_raster_bwd_headroom_bits")
+    assert not np.array_equal(g24, g30)                       # the second pass ran (another quantum)
+    assert util.rel_err(g24, g30) < 3e-4 and util.rel_err(g24, g_ref) < 1e-3
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib().acfm_set_raster_bwd_headroom_bits(31), "acfm_set_raster_bwd_headroom_bits")
+
+
 def test_backward_vs_oracle():
     """grad wrt screen vertices, then end to end through NeuralRenderer to vertices and cameras."""
     from acfm_video_3d_reconstruction_b200 import NeuralRenderer
