@@ -54,6 +54,8 @@ SIGNATURES = {
     "acfm_uv_sample_bwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_mask_sums_fwd": [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_mask_sums_bwd": [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp],
+    "acfm_mask_loss_combine_fwd": [_c_vp, _c_int, _c_int, _c_f, _c_f, _c_f, _c_vp, _c_vp],
+    "acfm_mask_loss_combine_bwd": [_c_vp, _c_vp, _c_int, _c_int, _c_f, _c_f, _c_f, _c_vp, _c_vp],
     "acfm_visible_verts": [_c_vp, _c_i64, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],
     "acfm_bds_loss_fwd": [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp],
     "acfm_bds_loss_bwd": [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp],

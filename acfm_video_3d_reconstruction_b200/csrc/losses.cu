@@ -66,7 +66,52 @@ __global__ void __launch_bounds__(kThreads) mask_sums_bwd_kernel(const float* __
   }
 }
 
+// per[n] = w_l1 * s0 / HW + w_iou * (1 - s1 / (s2 + 1e-6)) + w_edt * s3 / HW: l1_loss, iou_loss and edt_loss (reduce=False) of one
+// render from its four sums, weighted and added as the callers do (multiframe/main.py:644-645,715-716)
+__global__ void __launch_bounds__(kThreads) mask_loss_combine_kernel(const float* __restrict__ sums, int N, float inv_hw, float w_l1,
+                                                                     float w_iou, float w_edt, float* __restrict__ per) {
+  const int n = blockIdx.x * kThreads + threadIdx.x;
+  if (n >= N) return;
+  const float4 s = *reinterpret_cast<const float4*>(sums + (size_t)n * 4);
+  float v = w_l1 * (s.x * inv_hw) + w_edt * (s.w * inv_hw);
+  if (w_iou != 0.0f) v += w_iou * (1.0f - s.y / (s.z + 1e-6f));
+  per[n] = v;
+}
+__global__ void __launch_bounds__(kThreads) mask_loss_combine_bwd_kernel(const float* __restrict__ sums, const float* __restrict__ grad_per,
+                                                                         int N, float inv_hw, float w_l1, float w_iou, float w_edt,
+                                                                         float* __restrict__ grad_sums) {
+  const int n = blockIdx.x * kThreads + threadIdx.x;
+  if (n >= N) return;
+  const float4 s = *reinterpret_cast<const float4*>(sums + (size_t)n * 4);
+  const float g = grad_per[n], d = 1.0f / (s.z + 1e-6f);
+  *reinterpret_cast<float4*>(grad_sums + (size_t)n * 4) =
+      make_float4(g * w_l1 * inv_hw, -g * w_iou * d, g * w_iou * s.y * d * d, g * w_edt * inv_hw);
+}
+
 }  // namespace
+
+extern "C" int acfm_mask_loss_combine_fwd(const float* sums, int N, int HW, float w_l1, float w_iou, float w_edt, float* per,
+                                          void* stream) {
+  ACFM_REQUIRE(N >= 0 && HW > 0, ACFM_ERR_BAD_ARG, "acfm_mask_loss_combine_fwd: bad sizes");
+  if (N == 0) return ACFM_OK;
+  ACFM_REQUIRE(sums && per && (((uintptr_t)sums) & 15u) == 0, ACFM_ERR_BAD_ARG, "acfm_mask_loss_combine_fwd: null or misaligned pointer");
+  mask_loss_combine_kernel<<<(N + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(sums, N, 1.0f / (float)HW, w_l1, w_iou,
+                                                                                                  w_edt, per);
+  ACFM_LAUNCH_OK("mask_loss_combine_kernel");
+  return ACFM_OK;
+}
+
+extern "C" int acfm_mask_loss_combine_bwd(const float* sums, const float* grad_per, int N, int HW, float w_l1, float w_iou, float w_edt,
+                                          float* grad_sums, void* stream) {
+  ACFM_REQUIRE(N >= 0 && HW > 0, ACFM_ERR_BAD_ARG, "acfm_mask_loss_combine_bwd: bad sizes");
+  if (N == 0) return ACFM_OK;
+  ACFM_REQUIRE(sums && grad_per && grad_sums && ((((uintptr_t)sums) | ((uintptr_t)grad_sums)) & 15u) == 0, ACFM_ERR_BAD_ARG,
+               "acfm_mask_loss_combine_bwd: null or misaligned pointer");
+  mask_loss_combine_bwd_kernel<<<(N + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(sums, grad_per, N, 1.0f / (float)HW,
+                                                                                                      w_l1, w_iou, w_edt, grad_sums);
+  ACFM_LAUNCH_OK("mask_loss_combine_bwd_kernel");
+  return ACFM_OK;
+}
 
 extern "C" int acfm_mask_sums_fwd(const float* mask, const float* target, const float* edt, int N, int NB, int HW,
                                   float* sums, void* stream) {

@@ -75,6 +75,7 @@ __global__ void skin_bwd_delta_kernel(const float* __restrict__ Wm, const float*
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   if (k < Kh) {
     const float* g = gp + (size_t)b * V * 3;
+#pragma unroll 4
     for (int v = s; v < V; v += S) {
       const float w = Wm[(size_t)v * Kh + k];
       a0 = fmaf(w, g[v * 3], a0);
@@ -91,23 +92,36 @@ __global__ void skin_bwd_delta_kernel(const float* __restrict__ Wm, const float*
   }
 }
 
-// grad_W[v,k] = sum_b gp[b,v,:] . delta[b,k,:];  grad_mean[v,:] = sum_b gp[b,v,:].  one thread per (v,k)
+// grad_W[v,k] = sum_b gp[b,v,:] . delta[b,k,:];  grad_mean[v,:] = sum_b gp[b,v,:].  A warp owns 32 consecutive (v,k) entries,
+// the CTA's 8 warps each take every 8th frame and the partial sums meet in shared memory in a fixed order (one thread per
+// entry walking all frames was a chain of 64 L2 latencies on 4 warps per SM).
 __global__ void __launch_bounds__(256) skin_bwd_w_kernel(const float* __restrict__ gp, const float* __restrict__ delta,
                                                          int NB, int V, int Kh, float* __restrict__ grad_W,
                                                          float* __restrict__ grad_mean) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= V * Kh) return;
-  const int v = i / Kh, k = i - v * Kh;
+  __shared__ float red[8][32][4];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool live = i < V * Kh;
+  const int v = live ? i / Kh : 0, k = live ? i - v * Kh : 0;
   float acc = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-  for (int b = 0; b < NB; ++b) {
-    const float* g = gp + ((size_t)b * V + v) * 3;
-    const float* d = delta + ((size_t)b * Kh + k) * 3;
-    const float g0 = g[0], g1 = g[1], g2 = g[2];
-    acc = fmaf(g0, d[0], fmaf(g1, d[1], fmaf(g2, d[2], acc)));
-    m0 += g0; m1 += g1; m2 += g2;
+  if (live) {
+#pragma unroll 4
+    for (int b = sl; b < NB; b += 8) {
+      const float* g = gp + ((size_t)b * V + v) * 3;
+      const float* d = delta + ((size_t)b * Kh + k) * 3;
+      const float g0 = g[0], g1 = g[1], g2 = g[2];
+      acc = fmaf(g0, d[0], fmaf(g1, d[1], fmaf(g2, d[2], acc)));
+      m0 += g0; m1 += g1; m2 += g2;
+    }
   }
-  if (grad_W) grad_W[i] = acc;
-  if (grad_mean && k == 0) { grad_mean[v * 3] = m0; grad_mean[v * 3 + 1] = m1; grad_mean[v * 3 + 2] = m2; }
+  red[sl][lane][0] = acc; red[sl][lane][1] = m0; red[sl][lane][2] = m1; red[sl][lane][3] = m2;
+  __syncthreads();
+  if (sl == 0 && live) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { acc += red[j][lane][0]; m0 += red[j][lane][1]; m1 += red[j][lane][2]; m2 += red[j][lane][3]; }
+    if (grad_W) grad_W[i] = acc;
+    if (grad_mean && k == 0) { grad_mean[v * 3] = m0; grad_mean[v * 3 + 1] = m1; grad_mean[v * 3 + 2] = m2; }
+  }
 }
 
 // ---- handle weights: softmax over VERTICES per handle (MeshNet.get_lbs, mesh_net.py:597-599) -----------------
@@ -183,7 +197,7 @@ extern "C" int acfm_skin_bwd(const float* W, const float* delta, const float* gr
   ACFM_REQUIRE(grad_pred_v && (W || Kh == 0) && (delta || Kh == 0), ACFM_ERR_BAD_ARG, "acfm_skin_bwd: null input");
   cudaStream_t st = (cudaStream_t)stream;
   if (grad_delta && Kh > 0) {
-    const int Kx = ((Kh + 31) / 32) * 32, S = 256 / Kx;
+    const int Kx = ((Kh + 31) / 32) * 32, S = 1024 / Kx;  // (32 vertex slices at Kh <= 32: 20 dependent loads per thread, not 80)
     dim3 block(Kx, S);
     skin_bwd_delta_kernel<<<NB, block, sizeof(float) * 3 * Kx * S, st>>>(W, grad_pred_v, V, Kh, grad_delta);
     ACFM_LAUNCH_OK("skin_bwd_delta_kernel");
@@ -191,7 +205,7 @@ extern "C" int acfm_skin_bwd(const float* W, const float* delta, const float* gr
   if ((grad_W && Kh > 0) || grad_mean_v) {
     const int Kk = Kh > 0 ? Kh : 1;
     ACFM_REQUIRE(Kh > 0, ACFM_ERR_UNSUPPORTED, "acfm_skin_bwd: grad_mean_v with zero handles");
-    skin_bwd_w_kernel<<<(V * Kk + 255) / 256, 256, 0, st>>>(grad_pred_v, delta, NB, V, Kh, grad_W, grad_mean_v);
+    skin_bwd_w_kernel<<<(V * Kk + 31) / 32, 256, 0, st>>>(grad_pred_v, delta, NB, V, Kh, grad_W, grad_mean_v);
     ACFM_LAUNCH_OK("skin_bwd_w_kernel");
   }
   return ACFM_OK;

@@ -59,6 +59,40 @@ def losses_from_sums(s, pixels, with_edt=True):
     return out
 
 
+class _CombineMaskLosses(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sums, pixels, w_l1, w_iou, w_edt):
+        _lib.require_cuda(sums)
+        sums = F_._f32c(sums)
+        N = sums.shape[0]
+        per = torch.empty((N,), dtype=torch.float32, device=sums.device)
+        with torch.cuda.device(sums.device):
+            st = _lib.lib().acfm_mask_loss_combine_fwd(_lib.ptr(sums), N, pixels, w_l1, w_iou, w_edt, _lib.ptr(per), _lib.stream_of(sums))
+        _lib.check(st, "acfm_mask_loss_combine_fwd")
+        _lib.count()
+        ctx.save_for_backward(sums)
+        ctx.cfg = (pixels, w_l1, w_iou, w_edt)
+        return per
+
+    @staticmethod
+    def backward(ctx, grad_per):
+        sums, = ctx.saved_tensors
+        g = torch.empty_like(sums)
+        with torch.cuda.device(sums.device):
+            st = _lib.lib().acfm_mask_loss_combine_bwd(_lib.ptr(sums), _lib.ptr(F_._f32c(grad_per)), sums.shape[0], *ctx.cfg, _lib.ptr(g),
+                                                       _lib.stream_of(sums))
+        _lib.check(st, "acfm_mask_loss_combine_bwd")
+        _lib.count()
+        return g, None, None, None, None
+
+
+def combine_mask_losses(sums, pixels, w_l1=1.0, w_iou=0.0, w_edt=0.0):
+    """(N,4) sums -> (N,) w_l1 * l1_loss + w_iou * iou_loss + w_edt * edt_loss per render (reduce=False), the weighted sum the
+    callers form from the three losses (multiframe/main.py:644-645,715-716), in one kernel each way instead of a dozen
+    element-wise torch launches on N numbers."""
+    return _CombineMaskLosses.apply(sums, int(pixels), float(w_l1), float(w_iou), float(w_edt))
+
+
 def mask_losses(mask, target, edt=None):
     """All per-render silhouette losses in one pass over a rendered mask: dict(l1, iou_loss, edt) each (N,)."""
     return losses_from_sums(mask_sums(mask, target, edt), mask[0].numel() if mask.shape[0] else 1, edt is not None)

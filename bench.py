@@ -223,8 +223,7 @@ class HotPath:
         # also takes the visible-vertex map from the render (the boundary loss below)
         out = F_.soft_silhouette_losses(ndc, self.faces, cfg["img"], target, edt, F_.BLUR_SOFT, cfg["K"], F_.SIGMA, want_vis=full)
         mask, p2f, sums = out[0], out[1], out[4]
-        ls = loss_utils.losses_from_sums(sums, cfg["img"] * cfg["img"])
-        per = ls["l1"] + W_EDT * ls["edt"]
+        per = loss_utils.combine_mask_losses(sums, cfg["img"] * cfg["img"], w_l1=1.0, w_edt=W_EDT)   # l1 + W_EDT * edt per render
         if full:
             G, NB, T = cfg["G"], cfg["frames"], cfg["clip_frames"]
             self.vert2kp.grad = None

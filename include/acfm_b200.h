@@ -229,6 +229,14 @@ int acfm_mask_sums_fwd(const float* mask, const float* target, const float* edt,
 int acfm_mask_sums_bwd(const float* mask, const float* target, const float* edt, const float* grad_sums,
                        int N, int NB, int HW, float* grad_mask, void* stream);
 
+/* The weighted per-render silhouette loss from the four sums (of acfm_mask_sums_fwd or acfm_raster_fwd_train):
+ *   per[n] = w_l1 * s0 / HW + w_iou * (1 - s1 / (s2 + 1e-6)) + w_edt * s3 / HW
+ * = w_l1 l1_loss + w_iou iou_loss + w_edt edt_loss with reduce=False (multiframe/nnutils/loss_utils.py:18-32,72-77,245-253), added as
+ * the callers add them (multiframe/main.py:644-645,715-716).  bwd: grad_per (N) -> grad_sums (N,4).  sums / grad_sums 16-byte aligned. */
+int acfm_mask_loss_combine_fwd(const float* sums, int N, int HW, float w_l1, float w_iou, float w_edt, float* per, void* stream);
+int acfm_mask_loss_combine_bwd(const float* sums, const float* grad_per, int N, int HW, float w_l1, float w_iou, float w_edt,
+                               float* grad_sums, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Reprojection losses on the projected mesh (multiframe/nnutils/loss_utils.py; same file in monocular/).
  * `stride` arguments let the (N,V,3) output of acfm_project_fwd be used in place without slicing out xy.

@@ -24,7 +24,11 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers', 'launch__shared_mem_per_block_dynamic',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sectors_srcunit_tex_op_write.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
-        'sm__cycles_elapsed.max']
+        'sm__cycles_elapsed.max', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum', 'smsp__inst_executed_op_shared_atom.sum',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active']
 
 
 def to_bytes(v, unit):
@@ -84,6 +88,7 @@ def full(kind, kname):
     tj = os.path.join(PR, "traffic.json")
     d = json.load(open(tj)) if os.path.exists(tj) else {}
     d.setdefault("C2", {})[kname] = rd + wr
+    d["C2"][kname + "_sm_throughput_pct"] = float(vals['sm__throughput.avg.pct_of_peak_sustained_elapsed'][0].replace(",", ""))
     d["C2"][kname + "_source"] = f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch, {tag}"
     json.dump(d, open(tj, "w"), indent=1)
     print("wrote", kind)

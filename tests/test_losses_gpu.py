@@ -49,3 +49,24 @@ def test_mask_losses_hypothesis_broadcast_and_grad():
     np.testing.assert_allclose(out["iou_loss"].detach().cpu().numpy(), io.detach().numpy(), rtol=RTOL)
     np.testing.assert_allclose(out["edt"].detach().cpu().numpy(), el.detach().numpy(), rtol=RTOL)
     assert util.rel_err(pc.grad.cpu().numpy(), pd.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("w", [(1.0, 0.0, 0.1), (0.5, 2.0, 0.0), (0.0, 1.0, 3.0)])
+def test_combined_mask_loss_equals_the_three_losses(w):
+    """combine_mask_losses = w_l1 * l1_loss + w_iou * iou_loss + w_edt * edt_loss (reduce=False) formed from the four sums, values
+    and gradient to the sums against the same combination written with torch ops in fp64."""
+    from acfm_video_3d_reconstruction_b200 import loss_utils
+    gen = torch.Generator().manual_seed(7)
+    N, HW = 37, 96 * 96
+    sums = (torch.rand(N, 4, generator=gen) * HW * 0.3 + 1.0).cuda().requires_grad_(True)
+    gp = torch.randn(N, generator=gen).cuda()
+    per = loss_utils.combine_mask_losses(sums, HW, *w)
+    g, = torch.autograd.grad((per * gp).sum(), sums)
+    s64 = sums.detach().double().requires_grad_(True)
+    ref = w[0] * s64[:, 0] / HW + w[1] * (1 - s64[:, 1] / (s64[:, 2] + 1e-6)) + w[2] * s64[:, 3] / HW
+    g64, = torch.autograd.grad((ref * gp.double()).sum(), s64)
+    assert torch.allclose(per.double(), ref, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(g.double(), g64, rtol=1e-5, atol=1e-12)
+    ls = loss_utils.losses_from_sums(sums.detach(), HW)
+    assert torch.allclose(per, w[0] * ls["l1"] + w[1] * ls["iou_loss"] + w[2] * ls["edt"], rtol=1e-6, atol=1e-7)
+    assert loss_utils.combine_mask_losses(sums[:0], HW).shape == (0,)
