@@ -60,6 +60,7 @@ namespace {
 static_assert(kRegion / kTileW == 4 && (kRegion / kTileW) * (kRegion / kTileH) == 32, "a region is 4 x 8 tiles: one lane / one bit each");
 constexpr int kZBuckets = 64;  // depth buckets of the region face list (front-to-back evaluation order)
 constexpr int kQueue = 32;     // per-lane candidate queue depth (record ids, 1 byte each)
+constexpr int kQueue1 = 4;     // ... at which the K = 1 renders drain: their depth culls feed on fresh nearest depths
 
 struct RasterParams {
   const float* ndc;
@@ -287,6 +288,7 @@ struct FaceSetup {
   FaceB b;
   float bxmin, bxmax, bymin, bymax;
   float g[9];  // conservative edge equations (A,B,C) x 3
+  float zcull;  // hard renders (blur == 0): a depth no fragment of the face can be nearer than; else 0 (never culls)
 };
 
 __device__ __forceinline__ void setup_face(FaceSetup& s, int f, float x0, float y0, float z0, float x1, float y1, float z1,
@@ -295,7 +297,16 @@ __device__ __forceinline__ void setup_face(FaceSetup& s, int f, float x0, float 
   b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; b.x2 = x2; b.y2 = y2; b.z0 = z0; b.z1 = z1; b.z2 = z2;
   s.bxmin = fsub(fminf(fminf(x0, x1), x2), sq_blur); s.bxmax = fadd(fmaxf(fmaxf(x0, x1), x2), sq_blur);
   s.bymin = fsub(fminf(fminf(y0, y1), y2), sq_blur); s.bymax = fadd(fmaxf(fmaxf(y0, y1), y2), sq_blur);
-  b.den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), eps);  // bary denominator
+  const float area = edge_fn(x2, y2, x0, y0, x1, y1);
+  b.den = fadd(area, eps);  // bary denominator
+  // Depth cull of the hard renders (blur == 0: a fragment's pixel lies inside the face, so its barycentric weights are
+  // positive and add up to area / (area + eps) — to 1 when they are clipped and renormalised — and its depth is at least that
+  // sum times the nearest vertex's depth; the sum falls to 1/2 for faces barely above the degenerate-face threshold).  Margin
+  // 1e-5 relative: two orders of magnitude over the rounding of the weights.  With a blur band the weights extrapolate beyond
+  // the face and no such bound holds.
+  const float zmin = fminf(fminf(z0, z1), z2);
+  const float wsum = __fdividef(area, b.den);
+  s.zcull = (blur == 0.0f && zmin > 0.0f && wsum > 0.0f) ? zmin * fminf(wsum, 1.0f) * 0.99999f : 0.0f;
   b.yden = rcp_refined(b.den);
   const float ex01 = fsub(x1, x0), ey01 = fsub(y1, y0), ex02 = fsub(x2, x0), ey02 = fsub(y2, y0);
   const float ex12 = fsub(x2, x1), ey12 = fsub(y2, y1);
@@ -350,6 +361,7 @@ struct KSet {
   int far_slot;                 // slot of the farthest entry (full sets; exact unless stale)
   unsigned long long far_key;   // its key (depth bits << 32 | face), or an upper bound of it when stale
   bool stale;
+  float d1;                     // KT == 1: the set is this distance and far_key (all ones: empty); no shared memory
 };
 
 __device__ __forceinline__ unsigned umax3(unsigned a, unsigned b, unsigned c) { return max(max(a, b), c); }
@@ -482,7 +494,10 @@ __device__ __forceinline__ void list_insert(unsigned* lz, unsigned short* lf, fl
 // one accepted fragment into the lane's set (KT = 20) or list (any other K)
 template <int KT>
 __device__ __forceinline__ void frag_add(KSet& s, int K, unsigned zb, unsigned face, float sd) {
-  if constexpr (KT > 0) kset_add<KT>(s, K, zb, face, sd);
+  if constexpr (KT == 1) {  // the nearest fragment, in registers
+    const unsigned long long key = ((unsigned long long)zb << 32) | face;
+    if (key < s.far_key) { s.far_key = key; s.d1 = sd; }
+  } else if constexpr (KT > 0) kset_add<KT>(s, K, zb, face, sd);
   else list_insert(s.z, s.f, s.d, K, s.cnt, s.far_key, zb, face, sd);  // far_key holds the K-th key of a full list
 }
 
@@ -673,7 +688,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
       recA[j] = make_float4(s.bxmin, s.bxmax, s.bymin, s.bymax);
       recA[cap + j] = make_float4(s.g[0], s.g[1], s.g[2], s.g[3]);
       recA[2 * cap + j] = make_float4(s.g[4], s.g[5], s.g[6], s.g[7]);
-      recA[3 * cap + j] = make_float4(s.g[8], 0.f, 0.f, 0.f);
+      recA[3 * cap + j] = make_float4(s.g[8], s.zcull, 0.f, 0.f);
       recB[j] = make_float4(s.b.x0, s.b.y0, s.b.x1, s.b.y1);
       recB[cap + j] = make_float4(s.b.x2, s.b.y2, s.b.z0, s.b.z1);
       recB[2 * cap + j] = make_float4(s.b.z2, s.b.den, s.b.yden, __int_as_float(s.b.flags));
@@ -744,11 +759,17 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
 
     int qn = 0;
     ks.cnt = 0; ks.far_slot = 0; ks.far_key = 0xffffffffffffffffull; ks.stale = true;  // (room: nothing is too far)
-    // empty set: every depth slot "infinitely far" (rank pass), every rank slot a valid index (output pass)
-    for (int j = 0; j < KS; j += 4) {
-      *reinterpret_cast<uint4*>(ks.z + j) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      // rank table: filled by rank_entries() for the sets; the identity for the sorted lists
-      *reinterpret_cast<unsigned*>(ord + j) = KT > 0 ? 0u : 0x03020100u + 0x04040404u * (unsigned)(j >> 2);
+    ks.d1 = 0.0f;
+    // K = 1: depth beyond which no face can matter to the TILE any more (every pixel has a nearer fragment); refreshed after
+    // every drain of the queues, which is why these renders drain at depth kQueue1
+    unsigned tile_far = 0xffffffffu;
+    if constexpr (KT != 1) {
+      // empty set: every depth slot "infinitely far" (rank pass), every rank slot a valid index (output pass)
+      for (int j = 0; j < KS; j += 4) {
+        *reinterpret_cast<uint4*>(ks.z + j) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        // rank table: filled by rank_entries() for the sets; the identity for the sorted lists
+        *reinterpret_cast<unsigned*>(ord + j) = KT > 0 ? 0u : 0x03020100u + 0x04040404u * (unsigned)(j >> 2);
+      }
     }
 
     // (a)-(c): fill the per-lane queues face by face; drain them when one is full or the faces run out (one drain site)
@@ -769,11 +790,13 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
             hit = !(t_xlo > bb.y) && !(t_xhi < bb.x) && !(t_ylo > bb.w) && !(t_yhi < bb.z);
             if (hit) {
               const float4 ga = recA[cap + j], gb = recA[2 * cap + j];
-              const float gc = recA[3 * cap + j].x;
+              const float4 g3 = recA[3 * cap + j];
+              const float gc = g3.x;
               const float m0 = fmaf(ga.x, ga.x > 0.f ? t_xhi : t_xlo, fmaf(ga.y, ga.y > 0.f ? t_yhi : t_ylo, ga.z));
               const float m1 = fmaf(ga.w, ga.w > 0.f ? t_xhi : t_xlo, fmaf(gb.x, gb.x > 0.f ? t_yhi : t_ylo, gb.y));
               const float m2 = fmaf(gb.z, gb.z > 0.f ? t_xhi : t_xlo, fmaf(gb.w, gb.w > 0.f ? t_yhi : t_ylo, gc));
               hit = !(m0 < -1.0f) && !(m1 < -1.0f) && !(m2 < -1.0f);
+              if constexpr (KT == 1) hit = hit && !(__float_as_uint(g3.y) > tile_far);  // behind what every pixel already has
             }
           }
           m = __ballot_sync(0xffffffffu, hit);
@@ -785,14 +808,16 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         const int jj = cbase + __ffs(m) - 1;
         m &= m - 1;
         const float4 bb = recA[jj], ga = recA[cap + jj], gb = recA[2 * cap + jj];
-        const float gc = recA[3 * cap + jj].x;
+        const float4 g3 = recA[3 * cap + jj];
+        const float gc = g3.x;
         bool cand = valid && !(xf > bb.y) && !(xf < bb.x) && !(yf > bb.w) && !(yf < bb.z);
+        if constexpr (KT == 1) cand = cand && !(__float_as_uint(g3.y) > (unsigned)(ks.far_key >> 32));  // behind this pixel's fragment
         const float g0 = fmaf(ga.x, xf, fmaf(ga.y, yf, ga.z));
         const float g1 = fmaf(ga.w, xf, fmaf(gb.x, yf, gb.y));
         const float g2 = fmaf(gb.z, xf, fmaf(gb.w, yf, gc));
         cand = cand && !(g0 < -1.0f) && !(g1 < -1.0f) && !(g2 < -1.0f);
         if (cand) queue[(qn++) * 32 + lane] = (unsigned char)jj;
-        full = __any_sync(0xffffffffu, qn == kQueue);
+        full = __any_sync(0xffffffffu, qn == (KT == 1 ? kQueue1 : kQueue));
       }
       // (c) evaluate: each lane pops its own queue.  (Measured without gain: prefetching the next entry's record a round early;
       // letting a lane with an empty queue evaluate a candidate of its mirror lane (lane ^ 31) and hand the result back by
@@ -813,6 +838,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         }
       }
       qn = 0;
+      if constexpr (KT == 1) tile_far = __reduce_max_sync(0xffffffffu, valid ? (unsigned)(ks.far_key >> 32) : 0u);
     } while (more);
 
     // overflow: region faces without a record (face-uniform evaluation, set-up broadcast by shuffles)
@@ -827,6 +853,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         setup_face(s, f, gverts[i0 * 3], gverts[i0 * 3 + 1], gverts[i0 * 3 + 2], gverts[i1 * 3], gverts[i1 * 3 + 1],
                    gverts[i1 * 3 + 2], gverts[i2 * 3], gverts[i2 * 3 + 1], gverts[i2 * 3 + 2], p.blur, p.sq_blur, p.k_eps);
         hit = !(t_xlo > s.bxmax) && !(t_xhi < s.bxmin) && !(t_ylo > s.bymax) && !(t_yhi < s.bymin);
+        if constexpr (KT == 1) hit = hit && !(__float_as_uint(s.zcull) > tile_far);
       }
       unsigned m = __ballot_sync(0xffffffffu, hit);
       while (m) {
@@ -849,7 +876,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
     // ---- (d) depth order, blend, write ------------------------------------------------------------------
     const int npx = min(kTileW, p.W - tx0);
     const int nrows = min(kTileH, p.H - ty0);
-    const int cnt = ks.cnt;
+    const int cnt = KT == 1 ? (int)(ks.far_key != 0xffffffffffffffffull) : ks.cnt;
     const int cmax = __reduce_max_sync(0xffffffffu, cnt);
     if (cmax == 0) {
       for (int row = 0; row < nrows; ++row) {
@@ -859,13 +886,13 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
       if (p.mask && valid) p.mask[((long long)n * p.H + yi) * p.W + xi] = 0.0f;
       continue;
     }
-    if constexpr (KT > 0) {
+    if constexpr (KT > 1) {
       if (cmax > 1) rank_entries<KT>(ks.z, ks.f, ord, cnt, cmax);  // one entry: ord[0] = 0 from the reset above
     }
     if (p.vis && cnt > 0) {
       // visible vertices = vertices of the faces that are nearest at some pixel (the fi_maps -> unique -> scatter_ block
       // of bds_loss / optical_flow_loss, loss_utils.py:213-223,432-441): one lane per distinct face of the tile stores
-      const unsigned fv = ks.f[ord[0]];
+      const unsigned fv = KT == 1 ? (unsigned)ks.far_key & 0xffffu : (unsigned)ks.f[ord[0]];
       const unsigned peers = __match_any_sync(__activemask(), fv);
       if (__ffs(peers) - 1 == lane) {
         const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
@@ -879,7 +906,8 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
       for (int i = 0; i < cnt; ++i) {  // in depth order, like the reference's product (the bits of the mask do not depend on
                                        // the order in which the faces were met)
         // 1 - sigmoid(-d / sigma) = 1 / (1 + exp(-d / sigma)); fast exp / divide: ~2e-7 relative, the mask is held to 1e-5
-        alpha *= __fdividef(1.0f, 1.0f + __expf(-ks.d[ord[i]] * inv_sigma_neg));
+        const float di = KT == 1 ? ks.d1 : ks.d[ord[i]];
+        alpha *= __fdividef(1.0f, 1.0f + __expf(-di * inv_sigma_neg));
       }
       p.mask[((long long)n * p.H + yi) * p.W + xi] = 1.0f - alpha;
       if (p.loss_part) {
@@ -901,11 +929,44 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
       }
       if (lane == 0) { tsum[tbit * 4] = l0; tsum[tbit * 4 + 1] = l1; tsum[tbit * 4 + 2] = l2; tsum[tbit * 4 + 3] = l3; }
     }
-    cnts[lane] = (unsigned char)cnt;
-    __syncwarp();
     const long long row_stride = (long long)p.W * K;                       // elements between image rows
     const long long tbase = (((long long)n * p.H + ty0) * p.W + tx0) * K;  // first element of the tile
     const long long nF = (long long)n * p.F;
+    if constexpr (KT == 1) {
+      // K = 1: every lane writes its own pixel from its registers (a row of the tile is 64 / 32 / 32 contiguous bytes)
+      if (valid) {
+        const long long g = ((long long)n * p.H + yi) * p.W + xi;
+        const int fv = (int)((unsigned)ks.far_key & 0xffffu);
+        p.p2f[g] = cnt ? nF + fv : -1ll;
+        p.zbuf[g] = cnt ? __uint_as_float((unsigned)(ks.far_key >> 32)) : -1.f;
+        p.dists[g] = cnt ? ks.d1 : -1.f;
+        if (p.bary) {
+          // barycentrics of the fragment, recomputed from the face id with the operator sequence of the evaluation
+          float b0 = -1.f, b1 = -1.f, b2 = -1.f;
+          if (cnt) {
+            const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
+            const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
+            const float x0 = gverts[i0 * 3], y0 = gverts[i0 * 3 + 1], x1 = gverts[i1 * 3], y1 = gverts[i1 * 3 + 1];
+            const float x2 = gverts[i2 * 3], y2 = gverts[i2 * 3 + 1];
+            const float den = fadd(edge_fn(x2, y2, x0, y0, x1, y1), p.k_eps);
+            b0 = fdiv(edge_fn(xf, yf, x1, y1, x2, y2), den);
+            b1 = fdiv(edge_fn(xf, yf, x2, y2, x0, y0), den);
+            b2 = fdiv(edge_fn(xf, yf, x0, y0, x1, y1), den);
+            if (p.clip) {
+              b0 = b0 > 0.0f ? b0 : 0.0f; b1 = b1 > 0.0f ? b1 : 0.0f; b2 = b2 > 0.0f ? b2 : 0.0f;
+              float sw = fadd(fadd(b0, b1), b2);
+              sw = sw > 1e-5f ? sw : 1e-5f;
+              b0 = fdiv(b0, sw); b1 = fdiv(b1, sw); b2 = fdiv(b2, sw);
+            }
+          }
+          float* bo = p.bary + g * 3;
+          bo[0] = b0; bo[1] = b1; bo[2] = b2;
+        }
+      }
+      continue;
+    }
+    cnts[lane] = (unsigned char)cnt;
+    __syncwarp();
     if (p.vec_ok && (K & 3) == 0) {
       // p2f: two entries (16 B) per store; zbuf / dists: four entries (16 B) per store
       const int P2 = K >> 1, P4 = K >> 2;
@@ -1492,6 +1553,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
   rc = faces_i64 ? launch_fwd<NW, long long, KT>(p, smem, (int)ctas, overlap, st) : launch_fwd<NW, int, KT>(p, smem, (int)ctas, overlap, st)
   if (workspace && tune.only == 'f') rc = ACFM_OK;
   else if (nw == 8 && K == 20) ACFM_FWD_CASE(8, 20);  // the reference's faces_per_pixel: straight-line set operations
+  else if (nw == 8 && K == 1) ACFM_FWD_CASE(8, 1);    // its hard renders (texture branch, OF_NeuralRenderer): z-buffer in registers
   else if (nw == 8) ACFM_FWD_CASE(8, 0);
   else if (nw == 4) ACFM_FWD_CASE(4, 0);
 #undef ACFM_FWD_CASE
