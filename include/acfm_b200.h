@@ -123,8 +123,10 @@ int acfm_softmax_cols_bwd(const float* y, const float* grad_y, int V, int K, flo
  * workspace: optional device scratch of acfm_raster_fwd_workspace_bytes(N,H,W) bytes (16-byte aligned, contents
  *   irrelevant on entry; on return it holds the call's region work lists, which acfm_raster_soft_bwd can reuse).  With it the call classifies the (render, 32x32 region) units first and
  *   writes the -1 padding of the units the mesh cannot touch from a second kernel that runs concurrently with the
- *   rasterizer (forked from and joined back into `stream`; capturable in a CUDA graph).  NULL: one kernel does both.
- *   Results are identical either way.
+ *   rasterizer (both on `stream`, overlapped by programmatic dependent launch; capturable in a CUDA graph; no other stream or
+ *   event is created).  NULL: one kernel does both.  Results are identical either way.
+ * Limits: K <= 64; V, F <= 65535 and 12 V + 4 F bytes of staged mesh must fit one CTA's shared memory beside the per-pixel
+ *   sets (about V <= 10000 / F <= 20000 at K = 20); ACFM_ERR_UNSUPPORTED otherwise.
  * --------------------------------------------------------------------------------------------- */
 int acfm_raster_fwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                     int N, int V, int F, int H, int W, int K, float blur_radius, int clip_bary,

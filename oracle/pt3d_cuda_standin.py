@@ -21,6 +21,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libacfm_pt3d_standin.so")
 _lib = None
+last_bin_max = 0   # fullest bin of the last render_mask(check_overflow=True) call
 
 
 def lib():
@@ -64,8 +65,11 @@ class _Rasterize(torch.autograd.Function):
                                           _p(p2f), _p(zbuf), _p(dists), _p(bary), st)
         if rc:
             raise RuntimeError(f"acfm_standin_rasterize: cuda error {rc}")
-        if check_overflow and int(fpb.max()) > M:   # PyTorch3D prints "Bin size was too small ..." and drops faces; a baseline must not
-            raise RuntimeError(f"max_faces_per_bin={M} overflows: a bin holds {int(fpb.max())} faces")
+        if check_overflow:   # PyTorch3D prints "Bin size was too small ..." and drops faces; a baseline must not
+            global last_bin_max
+            last_bin_max = int(fpb.max())
+            if last_bin_max > M:
+                raise RuntimeError(f"max_faces_per_bin={M} overflows: a bin holds {last_bin_max} faces")
         ctx.save_for_backward(face_verts, p2f)
         ctx.mark_non_differentiable(p2f, zbuf, bary)
         return p2f, zbuf, bary, dists

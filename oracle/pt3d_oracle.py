@@ -218,9 +218,12 @@ def vertex_colors_as_texels(fr, colors, faces):
     return (bary[..., None] * c).sum(-2) * m[..., None]
 
 
-def atlas_shade(fr, atlas, sigma=SIGMA, gamma=1e-4, znear=1.0, zfar=100.0, eps=1e-10):
+def atlas_shade(fr, atlas, sigma=SIGMA, gamma=1e-4, znear=1.0, zfar=100.0, eps=1e-10, bg_texel="zero"):
     """TexturesAtlas.sample_textures + ambient-only Phong + softmax_rgb_blend: SURVEY.md §9.7.
-    atlas (N,F,T,T,3).  Returns imgs (N,3,H,W), sil (N,H,W)."""
+    atlas (N,F,T,T,3).  Returns imgs (N,3,H,W), sil (N,H,W).
+    bg_texel: what a padding fragment (pix_to_face = -1) samples — "zero" (texels masked, SURVEY §9.7's reading) or "wrap"
+    (python's atlas_packed[-1]: the last face's texel, unmasked; the other reading of the 0.3.0 source).  The blend gives
+    such fragments weight 0 either way; tests/test_oracle_variants.py asserts the images are identical."""
     p2f, bary, dists, zbuf = fr["pix_to_face"], fr["bary"], fr["dists"], fr["zbuf"]
     N, H, W, K = p2f.shape
     dt = dists.dtype
@@ -233,10 +236,12 @@ def atlas_shade(fr, atlas, sigma=SIGMA, gamma=1e-4, znear=1.0, zfar=100.0, eps=1
     below = (b.sum(-1) * dt.type(R) - wxy.astype(dt).sum(-1)) <= 1.0
     wx = np.where(below, wxy[..., 0], R - 1 - wxy[..., 0])
     wy = np.where(below, wxy[..., 1], R - 1 - wxy[..., 1])
-    fi = np.where(m, p2f, 0)
+    fi = np.where(m, p2f, 0 if bg_texel == "zero" else ap.shape[0] - 1)
     wx = np.clip(np.where(m, wx, 0), 0, R - 1)
     wy = np.clip(np.where(m, wy, 0), 0, R - 1)
-    texel = ap[fi, wy, wx] * m[..., None]                                   # (N,H,W,K,3)
+    texel = ap[fi, wy, wx]                                                  # (N,H,W,K,3)
+    if bg_texel == "zero":
+        texel = texel * m[..., None]
     return blend_texels(fr, texel, sigma, gamma, znear, zfar, eps)
 
 

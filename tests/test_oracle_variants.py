@@ -108,3 +108,20 @@ def test_k_epsilon_variant(renders):
     print(f"{shape}: kEpsilon 1e-8 -> 1e-30 reorders {order.sum()} of {covered.sum()} covered pixels "
           f"({100 * order.sum() / covered.sum():.1f} %), changes the kept set at {setdiff.sum()} "
           f"({100 * setdiff.sum() / covered.sum():.1f} %), max |mask change| {np.abs(base['mask'] - o['mask']).max():.3f}")
+
+
+def test_atlas_lookup_of_padding_fragments_is_immaterial():
+    """TexturesAtlas.sample_textures indexes the atlas with pix_to_face = -1 for padding fragments.  Whether that
+    reads zeros (masked) or the last face's texel (python's [-1]), softmax_rgb_blend gives those fragments weight 0: the
+    rendered image and silhouette are identical, bit for bit."""
+    from tests import util
+    v, f = util.template("bird")
+    N, S, R = 2, 96, 4
+    X, cam = util.synth_verts(v, N, seed=5), util.synth_cams(N, seed=6)
+    faces = np.repeat(f[None], N, 0)
+    fr = orc.hard_raster(X, faces, cam, img_size=S, offset_z=5.0)
+    assert (fr["pix_to_face"] < 0).mean() > 0.3 and (fr["pix_to_face"] >= 0).mean() > 0.05
+    atlas = np.random.default_rng(0).random((N, f.shape[0], R, R, 3)).astype(np.float32) + 0.5     # no zero texel anywhere
+    a = orc.atlas_shade(fr, atlas, bg_texel="zero")
+    b = orc.atlas_shade(fr, atlas, bg_texel="wrap")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
