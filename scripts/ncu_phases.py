@@ -1,6 +1,8 @@
 """Group the per-line output of ncu_lines.py into the phases of raster_fwd_kernel (line anchors read from the source)."""
 import re, sys
-src = open("acfm_video_3d_reconstruction_b200/csrc/raster_fwd.cu").read().splitlines()
+# second argument: the raster_fwd.cu the profiled library was built from (default: the working tree) — the line anchors must
+# come from the same source as the report
+src = open(sys.argv[2] if len(sys.argv) > 2 else "acfm_video_3d_reconstruction_b200/csrc/raster_fwd.cu").read().splitlines()
 def find(pat):
     for i, l in enumerate(src, 1):
         if pat in l: return i
