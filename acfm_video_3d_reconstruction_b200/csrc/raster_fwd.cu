@@ -93,6 +93,10 @@ struct RasterParams {
 // slots of the padding pattern: one region row at K, at least 640 (bulk stores below ~2.5 KB reach a third of the HBM write rate)
 __host__ __device__ inline int fill_pattern_slots(int K) { return max(kRegion * K, 640); }
 
+// which (K, CTA size) pairs run the K-nearest-set specialisation of the rasterizer kernel (KT = K); the others run the sorted
+// lists (KT = 0) or, for K = 1, the register z-buffer (KT = 1: the slab arrays are unused)
+__host__ __device__ inline bool fwd_sets(int K, int nwarps) { return K == 20 && nwarps == 8; }
+
 // shared-memory carve-up, identical on host and device
 struct FwdSmem {
   int off_ndc, off_red, off_hist, off_tw, off_ts, off_rlist, off_recA, off_recB, off_union, off_verts, off_tmp, warp_bytes, total;
@@ -112,10 +116,17 @@ struct FwdSmem {
     off_verts = o;
     const int vb = ((V * 12 + 16 + 15) / 16) * 16;
     off_tmp = o + vb;
-    // rows of K entries padded to 16 bytes of depth words with an ODD number of 16-byte chunks: a quarter warp's LDS.128
-    // of the same chunk index then falls into 8 distinct bank groups (the rank pass reads the depths four at a time)
-    KS = ((K + 3) / 4) * 4;
-    if (((KS / 4) & 1) == 0) KS += 4;
+    // K-nearest sets (K = 20 on 8-warp CTAs, see fwd_sets()): rows of K entries padded to 16 bytes of depth words with an
+    // ODD number of 16-byte chunks: a quarter warp's LDS.128 of the same chunk index then falls into 8 distinct bank groups
+    // (the rank pass reads the depths four at a time).  Sorted lists (every other K): an ODD row stride in words, so that the
+    // 32 lanes' 4-byte accesses at the same list position fall into 32 distinct banks (a stride of 52 words at K = 50 made
+    // every insertion step a 4-way conflict: half of all shared wavefronts of the C4 workload).
+    if (fwd_sets(K, nwarps)) {
+      KS = ((K + 3) / 4) * 4;
+      if (((KS / 4) & 1) == 0) KS += 4;
+    } else {
+      KS = K | 1;
+    }
     int w = 0;
     w_z = w; w += KS * 32 * 4;   // depth bits
     w_d = w; w += KS * 32 * 4;   // signed squared distance
@@ -763,12 +774,12 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
     // K = 1: depth beyond which no face can matter to the TILE any more (every pixel has a nearer fragment); refreshed after
     // every drain of the queues, which is why these renders drain at depth kQueue1
     unsigned tile_far = 0xffffffffu;
-    if constexpr (KT != 1) {
-      // empty set: every depth slot "infinitely far" (rank pass), every rank slot a valid index (output pass)
+    if constexpr (KT > 1) {
+      // empty set: every depth slot "infinitely far" (rank pass), every rank slot a valid index (output pass; filled by
+      // rank_entries()).  The sorted lists (KT = 0) need neither: their order is the slot order and cnt bounds every access.
       for (int j = 0; j < KS; j += 4) {
         *reinterpret_cast<uint4*>(ks.z + j) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        // rank table: filled by rank_entries() for the sets; the identity for the sorted lists
-        *reinterpret_cast<unsigned*>(ord + j) = KT > 0 ? 0u : 0x03020100u + 0x04040404u * (unsigned)(j >> 2);
+        *reinterpret_cast<unsigned*>(ord + j) = 0u;
       }
     }
 
@@ -892,7 +903,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
     if (p.vis && cnt > 0) {
       // visible vertices = vertices of the faces that are nearest at some pixel (the fi_maps -> unique -> scatter_ block
       // of bds_loss / optical_flow_loss, loss_utils.py:213-223,432-441): one lane per distinct face of the tile stores
-      const unsigned fv = KT == 1 ? (unsigned)ks.far_key & 0xffffu : (unsigned)ks.f[ord[0]];
+      const unsigned fv = KT == 1 ? (unsigned)ks.far_key & 0xffffu : (unsigned)ks.f[KT > 1 ? ord[0] : 0];
       const unsigned peers = __match_any_sync(__activemask(), fv);
       if (__ffs(peers) - 1 == lane) {
         const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
@@ -906,7 +917,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
       for (int i = 0; i < cnt; ++i) {  // in depth order, like the reference's product (the bits of the mask do not depend on
                                        // the order in which the faces were met)
         // 1 - sigmoid(-d / sigma) = 1 / (1 + exp(-d / sigma)); fast exp / divide: ~2e-7 relative, the mask is held to 1e-5
-        const float di = KT == 1 ? ks.d1 : ks.d[ord[i]];
+        const float di = KT == 1 ? ks.d1 : ks.d[KT > 1 ? ord[i] : i];
         alpha *= __fdividef(1.0f, 1.0f + __expf(-di * inv_sigma_neg));
       }
       p.mask[((long long)n * p.H + yi) * p.W + xi] = 1.0f - alpha;
@@ -979,7 +990,8 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         if (col >= npx || row >= nrows) continue;
         const int c = cnts[pxl];
         const int o = pxl * KS;
-        const unsigned so = *reinterpret_cast<const unsigned short*>(wo + o + k);  // two rank slots
+        // two rank slots (the sorted lists' order is the slot order)
+        const unsigned so = KT > 1 ? *reinterpret_cast<const unsigned short*>(wo + o + k) : (unsigned)(k | ((k + 1) << 8));
         const long long a = k < c ? nF + wf[o + (so & 0xffu)] : -1ll;
         const long long b = k + 1 < c ? nF + wf[o + (so >> 8)] : -1ll;
         longlong2 v; v.x = a; v.y = b;
@@ -992,8 +1004,11 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         if (col >= npx || row >= nrows) continue;
         const int c = cnts[pxl];
         const int o = pxl * KS;
-        const unsigned so = *reinterpret_cast<const unsigned*>(wo + o + k);  // four rank slots
-        const int s0 = o + (so & 0xffu), s1 = o + ((so >> 8) & 0xffu), s2 = o + ((so >> 16) & 0xffu), s3 = o + (so >> 24);
+        int s0 = o + k, s1 = s0 + 1, s2 = s0 + 2, s3 = s0 + 3;
+        if constexpr (KT > 1) {
+          const unsigned so = *reinterpret_cast<const unsigned*>(wo + o + k);  // four rank slots
+          s0 = o + (so & 0xffu); s1 = o + ((so >> 8) & 0xffu); s2 = o + ((so >> 16) & 0xffu); s3 = o + (so >> 24);
+        }
         float4 z, d;
         z.x = k < c ? __uint_as_float(wz[s0]) : -1.f; d.x = k < c ? wd[s0] : -1.f;
         z.y = k + 1 < c ? __uint_as_float(wz[s1]) : -1.f; d.y = k + 1 < c ? wd[s1] : -1.f;
@@ -1013,7 +1028,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         const int col = pxl & 7, row = pxl >> 3;
         if (col >= npx || row >= nrows) continue;
         const int c = cnts[pxl];
-        const int o = pxl * KS + wo[pxl * KS + k];
+        const int o = pxl * KS + (KT > 1 ? (int)wo[pxl * KS + k] : k);
         const long long g = tbase + row * row_stride + col * K + k;
         p.p2f[g] = k < c ? nF + wf[o] : -1ll;
         p.zbuf[g] = k < c ? __uint_as_float(wz[o]) : -1.f;
@@ -1030,7 +1045,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
         if (col >= npx || row >= nrows) continue;
         float b0 = -1.f, b1 = -1.f, b2 = -1.f;
         if (k < cnts[pxl]) {
-          const int fv = (int)wf[pxl * KS + wo[pxl * KS + k]];
+          const int fv = (int)wf[pxl * KS + (KT > 1 ? (int)wo[pxl * KS + k] : k)];
           const IdxT* fp = reinterpret_cast<const IdxT*>(p.faces) + fbase + (long long)fv * 3;
           const int i0 = (int)fp[0], i1 = (int)fp[1], i2 = (int)fp[2];
           const float x0 = gverts[i0 * 3], y0 = gverts[i0 * 3 + 1], x1 = gverts[i1 * 3], y1 = gverts[i1 * 3 + 1];
@@ -1552,7 +1567,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
 #define ACFM_FWD_CASE(NW, KT)                                                                          \
   rc = faces_i64 ? launch_fwd<NW, long long, KT>(p, smem, (int)ctas, overlap, st) : launch_fwd<NW, int, KT>(p, smem, (int)ctas, overlap, st)
   if (workspace && tune.only == 'f') rc = ACFM_OK;
-  else if (nw == 8 && K == 20) ACFM_FWD_CASE(8, 20);  // the reference's faces_per_pixel: straight-line set operations
+  else if (fwd_sets(K, nw)) ACFM_FWD_CASE(8, 20);  // the reference's faces_per_pixel: straight-line set operations
   else if (nw == 8 && K == 1) ACFM_FWD_CASE(8, 1);    // its hard renders (texture branch, OF_NeuralRenderer): z-buffer in registers
   else if (nw == 8) ACFM_FWD_CASE(8, 0);
   else if (nw == 4) ACFM_FWD_CASE(4, 0);
