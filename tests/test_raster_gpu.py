@@ -601,3 +601,39 @@ def test_outputs_are_written_inside_their_bounds_only(S, K):
         _lib.check(st, "acfm_raster_soft_bwd")
         torch.cuda.synchronize()
         assert (bg[:G] == 123.0).all() and (bg[-G:] == 123.0).all() and (g != 123.0).all() and g.view(N, -1)[1].abs().sum() == 0
+
+
+@pytest.mark.parametrize("clip,blur", [(False, 0.0), (True, 0.0), (False, 2e-3)])
+def test_hard_render_depth_culls_are_exact(clip, blur):
+    """K = 1 keeps the nearest fragment in registers and drops faces whose nearest vertex lies behind what a pixel (or a whole
+    tile) already has.  The bound behind that cull — fragment depth >= (sum of the barycentric weights) x (nearest vertex depth)
+    — is stressed here: large faces in the back, thousands of tiny faces barely above the degenerate-face threshold in front of
+    and behind them (their weights add up to as little as 1/2, so their fragments are NEARER than their nearest vertex), faces
+    crossing z = 0, and a blur band (where the cull must switch itself off).  Bit-exact against the oracle."""
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    gen = torch.Generator().manual_seed(17 + int(clip) + int(blur * 1e4))
+    N, S = 3, 96
+    nbig, ntiny = 60, 1500
+    F = nbig + ntiny
+    V = 3 * F
+    c_big = torch.rand(N, nbig, 1, 2, generator=gen) * 2 - 1
+    big = c_big + 0.5 * torch.randn(N, nbig, 3, 2, generator=gen)
+    # tiny faces AROUND pixel centres (x = 1 - (2 i + 1) / S), so that they do own pixels: circumradius 6e-5 .. 2e-3, i.e. areas of
+    # 5e-9 .. 5e-6 against kEpsilon = 1e-8
+    c_tiny = 1.0 - (2.0 * torch.randint(0, S, (N, ntiny, 1, 2), generator=gen).float() + 1.0) / S
+    size = 10 ** (torch.rand(N, ntiny, 1, 1, generator=gen) * 1.5 - 4.2)
+    ang = torch.rand(N, ntiny, 1, generator=gen) * 6.2832 + torch.tensor([0.0, 2.0944, 4.1888])
+    tiny = c_tiny + size * torch.stack([torch.cos(ang), torch.sin(ang)], -1) * (1.0 + 0.3 * torch.rand(N, ntiny, 3, 1, generator=gen))
+    xy = torch.cat([big, tiny], 1).reshape(N, V, 2)
+    z_big = torch.rand(N, nbig, 3, 1, generator=gen) * 2.0 + 0.5
+    z_big[:, ::9] -= 1.5                                                          # some cross z = 0
+    z_tiny = torch.rand(N, ntiny, 1, 1, generator=gen) * 3.0 + 0.05 + 0.3 * torch.rand(N, ntiny, 3, 1, generator=gen)
+    z = torch.cat([z_big, z_tiny], 1).reshape(N, V, 1)
+    ndc = torch.cat([xy, z], -1).numpy().astype(np.float32)
+    faces = np.repeat(np.arange(V, dtype=np.int64).reshape(1, F, 3), N, 0)
+    ref = orc.rasterize(ndc, faces, S, blur, 1, clip_bary=clip, want_bary=True)
+    out = F_.rasterize(torch.from_numpy(ndc).cuda(), torch.from_numpy(faces).cuda(), S, blur, 1, clip_barycentric_coords=clip, want_bary=True)
+    _assert_fragments_equal(out, ref)
+    assert np.array_equal(out["bary"].cpu().numpy(), ref["bary"])
+    hit = ref["pix_to_face"][..., 0] % F
+    assert (ref["pix_to_face"] >= 0).mean() > 0.5 and ((hit >= nbig) & (ref["pix_to_face"][..., 0] >= 0)).sum() > 50   # tiny faces do win pixels
