@@ -40,6 +40,11 @@ SIGNATURES = {
                               _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp],
     "acfm_raster_soft_bwd_train": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp, _c_vp,
                                    _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp],
+    "acfm_raster_lean_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
+    "acfm_raster_fwd_lean": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_vp, _c_vp,
+                             _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp],
+    "acfm_raster_soft_bwd_lean": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_vp, _c_vp,
+                                  _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_soft_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f,
                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp],
     "acfm_raster_dists_bwd": [_c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp,
@@ -98,7 +103,7 @@ def lib():
             fn.argtypes = argtypes
             fn.restype = (ctypes.c_char_p if name == "acfm_last_error_string" else
                           ctypes.c_int64 if name in ("acfm_raster_fwd_workspace_bytes", "acfm_handle_solve_workspace_bytes",
-                                                    "acfm_raster_loss_workspace_bytes") else
+                                                    "acfm_raster_loss_workspace_bytes", "acfm_raster_lean_workspace_bytes") else
                           ctypes.c_float if name == "acfm_get_raster_epsilon" else ctypes.c_int)
         if os.environ.get("ACFM_NVTX", "0") not in ("", "0"):
             l = _NvtxLib(l)   # every C-ABI call becomes an NVTX range named after the entry point (nsys / ncu --nvtx)

@@ -49,6 +49,9 @@ struct BwdParams {
   float* grad_ndc;
   int regions_x, regions_y;
   const int* work;  // optional: the forward's work lists (live regions by weight class); NULL = every region
+  // lean mode: the forward's compact fragments [work-list slot][pixel of the region][K] instead of p2f / dists
+  const unsigned short* lean_f;
+  const float* lean_d;
 };
 
 struct BwdSmem {
@@ -168,7 +171,7 @@ __device__ __forceinline__ float upstream_grad(const BwdParams& p, int n, long l
 // otherwise it is d loss / d dists per fragment (texture branch, general rasterize_meshes backward on dists).
 // (71 registers, 22.6 KB of shared memory at the reference's templates: 7 CTAs per SM.  Capped at 63 registers for 8: no change;
 // at 56 for 9: 0.42 -> 0.50 ms at C2.)
-template <typename IdxT, bool FROM_MASK>
+template <typename IdxT, bool FROM_MASK, bool LEAN = false>
 __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p) {
   constexpr int NT = 128, NWARPS = 4;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int regions = p.regions_x * p.regions_y;
   int unit = blockIdx.x;
+  const size_t slot = blockIdx.x;  // position in the work lists: where the lean forward put this region's fragments
   if (p.work) {
     // the regions the forward found live (the others hold no fragment: nothing to differentiate), heaviest first — same
     // lists, same layout as raster_fwd_kernel reads (raster_fwd.cu: {.., live per weight class [4] at [4], lists at [8]})
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(128) raster_soft_bwd_kernel(const BwdParams p)
   AccFixed accx{reinterpret_cast<int*>(acci), fx_scale, gout, true};
   AccFloat accl{accf};
   const int nchunks = (na + 31) / 32;
-  const bool vec = (K & 3) == 0 && (((uintptr_t)p.p2f | (uintptr_t)p.dists | (FROM_MASK ? 0 : (uintptr_t)p.grad_dists)) & 15u) == 0;
+  const bool vec = LEAN || ((K & 3) == 0 && (((uintptr_t)p.p2f | (uintptr_t)p.dists | (FROM_MASK ? 0 : (uintptr_t)p.grad_dists)) & 15u) == 0);
   int passes = 1;
 pass_again:
   while (true) {
@@ -282,9 +286,22 @@ pass_again:
     const long long pix = ((long long)n * p.H + yi) * p.W + xi;
     // pixel centre (PixToNdc); 2 ulp is plenty for the backward
     const float xf = fmaf((float)(2 * (p.W - 1 - xi) + 1), inv_w, -1.0f), yf = fmaf((float)(2 * (p.H - 1 - yi) + 1), inv_h, -1.0f);
-    const long long* pf = p.p2f + pix * K;
-    const float* pd = p.dists + pix * K;
-    const long long nF = (long long)n * p.F;
+    const long long* pf = LEAN ? nullptr : p.p2f + pix * K;
+    const float* pd = LEAN ? p.lean_d + (slot * (kRegion * kRegion) + i) * K : p.dists + pix * K;
+    const unsigned short* lf = LEAN ? p.lean_f + (slot * (kRegion * kRegion) + i) * K : nullptr;
+    const long long nF = LEAN ? 0 : (long long)n * p.F;
+    // one group of four fragment ids: packed ids n F + f (-1: none), or, lean, the render's own face ids (0xffff: none) widened
+    auto load_ids = [&](int g4, longlong2& a, longlong2& b) {
+      if constexpr (LEAN) {
+        const uint2 w = *reinterpret_cast<const uint2*>(lf + 4 * g4);
+        const unsigned f0 = w.x & 0xffffu, f1 = w.x >> 16, f2 = w.y & 0xffffu, f3 = w.y >> 16;
+        a.x = f0 == 0xffffu ? -1ll : (long long)f0; a.y = f1 == 0xffffu ? -1ll : (long long)f1;
+        b.x = f2 == 0xffffu ? -1ll : (long long)f2; b.y = f3 == 0xffffu ? -1ll : (long long)f3;
+      } else {
+        a = *reinterpret_cast<const longlong2*>(pf + 4 * g4);
+        b = *reinterpret_cast<const longlong2*>(pf + 4 * g4 + 2);
+      }
+    };
     // fragments in groups of four (16-byte loads); the first group's loads are issued before the upstream gradient is formed
     // and every later group's while the one before it is processed: the kernel is bound by the latency of these loads and of
     // the shared atomics, so one group is always in flight.  Lanes start at different groups so that neighbouring pixels,
@@ -294,8 +311,7 @@ pass_again:
     longlong2 fa = make_longlong2(-1, -1), fb = fa;
     float4 dd = make_float4(0.f, 0.f, 0.f, 0.f), gg = dd;
     if (vec) {
-      fa = *reinterpret_cast<const longlong2*>(pf + 4 * g);
-      fb = *reinterpret_cast<const longlong2*>(pf + 4 * g + 2);
+      load_ids(g, fa, fb);
       dd = *reinterpret_cast<const float4*>(pd + 4 * g);
       if (!FROM_MASK) gg = *reinterpret_cast<const float4*>(p.grad_dists + pix * K + 4 * g);
     }
@@ -318,8 +334,7 @@ pass_again:
         const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
         g = (g + 1 == groups) ? 0 : g + 1;
         if (s + 1 < groups) {  // next group: in flight during this one's arithmetic
-          fa = *reinterpret_cast<const longlong2*>(pf + 4 * g);
-          fb = *reinterpret_cast<const longlong2*>(pf + 4 * g + 2);
+          load_ids(g, fa, fb);
           dd = *reinterpret_cast<const float4*>(pd + 4 * g);
           if (!FROM_MASK) gg = *reinterpret_cast<const float4*>(p.grad_dists + pix * K + 4 * g);
         }
@@ -388,12 +403,15 @@ namespace {
 int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,
                int N, int V, int F, int H, int W, int K, float sigma, const int64_t* pix_to_face, const float* dists,
                const float* mask, const float* grad_mask, const float* grad_dists, float* grad_ndc, const void* work, void* stream,
-               const float* grad_sums = nullptr, const float* loss_target = nullptr, const float* loss_edt = nullptr, int NB = 1) {
+               const float* grad_sums = nullptr, const float* loss_target = nullptr, const float* loss_edt = nullptr, int NB = 1,
+               const void* lean_workspace = nullptr) {
   ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0 && K >= 1, ACFM_ERR_BAD_ARG, "%s: bad sizes", who);
   ACFM_REQUIRE(!from_mask || sigma > 0.0f, ACFM_ERR_BAD_ARG, "%s: sigma must be > 0", who);
   ACFM_REQUIRE(faces_batch_stride == 0 || faces_batch_stride == (int64_t)F * 3, ACFM_ERR_BAD_ARG, "%s: faces_batch_stride must be 0 or F*3", who);
   if (N == 0 || V == 0) return ACFM_OK;
-  ACFM_REQUIRE(ndc && faces && pix_to_face && dists && grad_ndc, ACFM_ERR_BAD_ARG, "%s: null pointer", who);
+  const bool lean = lean_workspace != nullptr;
+  ACFM_REQUIRE(ndc && faces && grad_ndc && (lean || (pix_to_face && dists)), ACFM_ERR_BAD_ARG, "%s: null pointer", who);
+  ACFM_REQUIRE(!lean || (from_mask && work && (K & 3) == 0), ACFM_ERR_BAD_ARG, "%s: the lean backward needs the forward's workspace", who);
   ACFM_REQUIRE(from_mask ? (mask && (grad_mask || grad_sums)) : (grad_dists != nullptr), ACFM_ERR_BAD_ARG, "%s: null gradient pointer", who);
   ACFM_REQUIRE(!grad_sums || (loss_target && NB > 0 && N % NB == 0), ACFM_ERR_BAD_ARG, "%s: fused losses need the target and N %% NB == 0", who);
   ACFM_REQUIRE(F <= 65535 && V <= 65535, ACFM_ERR_UNSUPPORTED, "%s: V=%d, F=%d must be <= 65535", who, V, F);
@@ -409,6 +427,11 @@ int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* fa
   p.grad_sums = grad_sums; p.loss_target = loss_target; p.loss_edt = loss_edt; p.NB = NB > 0 ? NB : 1;
   p.work = (const int*)work;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
+  {
+    const long long U = (long long)N * p.regions_x * p.regions_y;
+    p.lean_d = (const float*)lean_workspace;                                            // layout: acfm_raster_fwd_lean
+    p.lean_f = lean ? (const unsigned short*)((const float*)lean_workspace + U * (kRegion * kRegion) * K) : nullptr;
+  }
   const BwdSmem L(V, F);
   ACFM_REQUIRE(L.total <= 227 * 1024, ACFM_ERR_UNSUPPORTED, "%s: needs %d B of shared memory (max 232448)", who, L.total);
   const long long ctas = (long long)N * p.regions_x * p.regions_y;
@@ -419,8 +442,16 @@ int launch_bwd(const char* who, bool from_mask, const float* ndc, const void* fa
     ACFM_CUDA_OK(acfm_ensure_smem(raster_soft_bwd_kernel<IDX, FM>, L.total, smem_set));                                \
     raster_soft_bwd_kernel<IDX, FM><<<(int)ctas, 128, L.total, st>>>(p);                                               \
   } while (0)
-  if (faces_i64) { if (from_mask) ACFM_LAUNCH_BWD(long long, true); else ACFM_LAUNCH_BWD(long long, false); }
+#define ACFM_LAUNCH_BWD_LEAN(IDX)                                                                                      \
+  do {                                                                                                                 \
+    static std::atomic<int> smem_set[kAcfmMaxDevices];                                                                 \
+    ACFM_CUDA_OK(acfm_ensure_smem(raster_soft_bwd_kernel<IDX, true, true>, L.total, smem_set));                        \
+    raster_soft_bwd_kernel<IDX, true, true><<<(int)ctas, 128, L.total, st>>>(p);                                       \
+  } while (0)
+  if (lean) { if (faces_i64) ACFM_LAUNCH_BWD_LEAN(long long); else ACFM_LAUNCH_BWD_LEAN(int); }
+  else if (faces_i64) { if (from_mask) ACFM_LAUNCH_BWD(long long, true); else ACFM_LAUNCH_BWD(long long, false); }
   else { if (from_mask) ACFM_LAUNCH_BWD(int, true); else ACFM_LAUNCH_BWD(int, false); }
+#undef ACFM_LAUNCH_BWD_LEAN
 #undef ACFM_LAUNCH_BWD
   ACFM_LAUNCH_OK("raster_soft_bwd_kernel");
   return ACFM_OK;
@@ -442,6 +473,15 @@ extern "C" int acfm_raster_soft_bwd_train(const float* ndc, const void* faces, i
                                           void* stream) {
   return launch_bwd("acfm_raster_soft_bwd_train", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma,
                     pix_to_face, dists, mask, grad_mask, nullptr, grad_ndc, fwd_workspace, stream, grad_sums, target, edt, NB);
+}
+
+extern "C" int acfm_raster_soft_bwd_lean(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V,
+                                         int F, int H, int W, int K, float sigma, const float* mask, const float* grad_mask,
+                                         const float* grad_sums, const float* target, const float* edt, int NB, float* grad_ndc,
+                                         const void* lean_workspace, const void* fwd_workspace, void* stream) {
+  ACFM_REQUIRE(lean_workspace && fwd_workspace, ACFM_ERR_BAD_ARG, "acfm_raster_soft_bwd_lean: needs the lean workspace and the workspace of the forward call");
+  return launch_bwd("acfm_raster_soft_bwd_lean", true, ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, sigma, nullptr,
+                    nullptr, mask, grad_mask, nullptr, grad_ndc, fwd_workspace, stream, grad_sums, target, edt, NB, lean_workspace);
 }
 
 extern "C" int acfm_raster_dists_bwd(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride,

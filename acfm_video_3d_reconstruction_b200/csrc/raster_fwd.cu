@@ -86,6 +86,10 @@ struct RasterParams {
   const float* loss_edt;     // (NB,H,W) or NULL
   int NB;
   float* loss_part;          // (N * regions, 4), zeroed by the host entry
+  // lean mode (acfm_raster_fwd_lean): no fragment tensors; the fragments of the live regions go, compact, to the caller's
+  // scratch for the backward: [work-list slot][pixel of the region (1024)][K] face ids (0xffff: none) and signed distances
+  unsigned short* lean_f;
+  float* lean_d;
   const int* work;  // split path, written by raster_prep_kernel: {live, fill runs, empty regions, -, live per weight class [4],
                     //   listR[4][N*regions], listF[N*regions][2]}
 };
@@ -542,8 +546,8 @@ __device__ __forceinline__ const float* raster_stage_verts(unsigned char* buf, c
 }
 
 // One (render, 32x32 region) unit, executed by the NWARPS rasterizer warps of a CTA (threads 0 .. NWARPS*32-1).
-template <int NWARPS, typename IdxT, int KT>
-__device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char* smem, const int unit) {
+template <int NWARPS, typename IdxT, int KT, bool LEAN = false>
+__device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char* smem, const int unit, const int slot = 0) {
   constexpr int NT = NWARPS * 32;
   const FwdSmem L(p.V, p.F, p.K, NWARPS, p.cap);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -609,7 +613,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
     const bool outside = (r_xlo > fadd(xmax, p.sq_blur)) || (r_xhi < fsub(xmin, p.sq_blur)) ||
                          (r_ylo > fadd(ymax, p.sq_blur)) || (r_yhi < fsub(ymin, p.sq_blur));
     if (outside) {
-      cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);
+      if constexpr (!LEAN) cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);  // (lean: the mask was cleared by the host entry)
       return;
     }
   }
@@ -658,7 +662,7 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
   raster_sync<NT>();
   const int nlist = *rcount;
   if (nlist == 0) {
-    cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);
+    if constexpr (!LEAN) cta_fill_rect<NWARPS>(p, n, px0, px1, py0, py1, warp, lane);
     return;
   }
   if (warp == 0) {  // exclusive scan of the 64 bucket counts
@@ -890,11 +894,13 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
     const int cnt = KT == 1 ? (int)(ks.far_key != 0xffffffffffffffffull) : ks.cnt;
     const int cmax = __reduce_max_sync(0xffffffffu, cnt);
     if (cmax == 0) {
-      for (int row = 0; row < nrows; ++row) {
-        const long long pix = ((long long)n * p.H + ty0 + row) * p.W + tx0;
-        warp_fill_frag(p, pix * K, npx * K, lane);
+      if constexpr (!LEAN) {
+        for (int row = 0; row < nrows; ++row) {
+          const long long pix = ((long long)n * p.H + ty0 + row) * p.W + tx0;
+          warp_fill_frag(p, pix * K, npx * K, lane);
+        }
+        if (p.mask && valid) p.mask[((long long)n * p.H + yi) * p.W + xi] = 0.0f;
       }
-      if (p.mask && valid) p.mask[((long long)n * p.H + yi) * p.W + xi] = 0.0f;
       continue;
     }
     if constexpr (KT > 1) {
@@ -974,6 +980,29 @@ __device__ __forceinline__ void raster_unit(const RasterParams& p, unsigned char
           bo[0] = b0; bo[1] = b1; bo[2] = b2;
         }
       }
+      continue;
+    }
+    if constexpr (LEAN) {
+      // compact fragments for the backward: K face ids (2 B) and K distances per pixel of the region, in depth order, 0xffff
+      // beyond cnt.  Pixels without a fragment have mask 0 and are never read back: nothing is written for them.
+      // Every lane writes its own pixel with 16-byte stores (K = 20: 40 B of ids, 80 B of distances; rows are 8-byte / 16-byte
+      // aligned: K * 2 and K * 4 bytes per pixel).
+      if (valid && cnt > 0) {
+        const size_t pixr = (size_t)slot * (kRegion * kRegion) + (size_t)(ly0 + (lane >> 3)) * kRegion + (lx0 + (lane & 7));
+        unsigned short* of = p.lean_f + pixr * K;
+        float* od = p.lean_d + pixr * K;
+#pragma unroll
+        for (int k = 0; k < KT; k += 4) {
+          const unsigned so = *reinterpret_cast<const unsigned*>(ord + k);
+          const int s0 = so & 0xffu, s1 = (so >> 8) & 0xffu, s2 = (so >> 16) & 0xffu, s3 = so >> 24;
+          const unsigned f0 = k < cnt ? ks.f[s0] : 0xffffu, f1 = k + 1 < cnt ? ks.f[s1] : 0xffffu;
+          const unsigned f2 = k + 2 < cnt ? ks.f[s2] : 0xffffu, f3 = k + 3 < cnt ? ks.f[s3] : 0xffffu;
+          *reinterpret_cast<uint2*>(of + k) = make_uint2(f0 | (f1 << 16), f2 | (f3 << 16));
+          *reinterpret_cast<float4*>(od + k) = make_float4(k < cnt ? ks.d[s0] : 0.f, k + 1 < cnt ? ks.d[s1] : 0.f,
+                                                          k + 2 < cnt ? ks.d[s2] : 0.f, k + 3 < cnt ? ks.d[s3] : 0.f);
+        }
+      }
+      __syncwarp();  // the sets are reused by the next tile
       continue;
     }
     cnts[lane] = (unsigned char)cnt;
@@ -1162,7 +1191,7 @@ __global__ void __maxnreg__(40) raster_fill_kernel(const RasterParams p, const i
 }
 
 // One CTA (NWARPS warps) per (render, region) unit.
-template <int NWARPS, typename IdxT, int KT>
+template <int NWARPS, typename IdxT, int KT, bool LEAN = false>
 __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 112 : 112) raster_fwd_kernel(const RasterParams p) {
   // (112 registers: two 8-warp CTAs leave every SM sub-partition room for one padding warp beside its four rasterizer warps)
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1186,7 +1215,7 @@ __global__ void __launch_bounds__(NWARPS * 32) __maxnreg__(NWARPS <= 8 ? 112 : 1
       *reinterpret_cast<int*>(smem + 12) = 0;  // next_tile
     }
     __syncthreads();
-    raster_unit<NWARPS, IdxT, KT>(p, smem, unit);
+    raster_unit<NWARPS, IdxT, KT, LEAN>(p, smem, unit, (int)blockIdx.x);  // (slot = position in the work lists)
   }
   // the grid completes only after the padding kernel has (see above): one thread of the last CTA waits for it
   if (p.work && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1215,9 +1244,9 @@ int fwd_pick_config(int V, int F, int K, int* smem_bytes, int* cap_out) {
   return best_nw;
 }
 
-template <int NWARPS, typename IdxT, int KT>
+template <int NWARPS, typename IdxT, int KT, bool LEAN = false>
 int launch_fwd(const RasterParams& p, int smem, int ctas, bool overlap, cudaStream_t st) {
-  auto kern = raster_fwd_kernel<NWARPS, IdxT, KT>;
+  auto kern = raster_fwd_kernel<NWARPS, IdxT, KT, LEAN>;
   static std::atomic<int> smem_set[kAcfmMaxDevices];
   ACFM_CUDA_OK(acfm_ensure_smem(kern, smem, smem_set));
   cudaLaunchConfig_t cfg = {};
@@ -1445,7 +1474,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
                     int W, int K, float blur_radius, int clip_bary, int cull_backfaces, float sigma, int64_t* pix_to_face,
                     float* zbuf, float* dists, float* bary, float* mask, float* visible_verts, const float* loss_target,
                     const float* loss_edt, int NB, float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes,
-                    void* workspace, int64_t workspace_bytes, void* stream);
+                    void* workspace, int64_t workspace_bytes, void* stream, void* lean_workspace = nullptr, int64_t lean_bytes = 0);
 }
 
 extern "C" int acfm_raster_fwd_launch_info(int N, int V, int F, int H, int W, int K, int* smem_bytes, int* num_ctas,
@@ -1492,7 +1521,8 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
                     int W, int K, float blur_radius, int clip_bary, int cull_backfaces, float sigma, int64_t* pix_to_face,
                     float* zbuf, float* dists, float* bary, float* mask, float* visible_verts, const float* loss_target,
                     const float* loss_edt, int NB, float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes,
-                    void* workspace, int64_t workspace_bytes, void* stream) {
+                    void* workspace, int64_t workspace_bytes, void* stream, void* lean_workspace, int64_t lean_bytes) {
+  const bool lean = lean_workspace != nullptr;
   ACFM_REQUIRE(N >= 0 && V >= 0 && F >= 0 && H > 0 && W > 0, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: bad sizes N=%d V=%d F=%d H=%d W=%d", N, V, F, H, W);
   ACFM_REQUIRE(K >= 1, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: faces_per_pixel K=%d must be >= 1", K);
   ACFM_REQUIRE(K <= 64, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: faces_per_pixel K=%d > 64 is not supported", K);
@@ -1500,7 +1530,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
   ACFM_REQUIRE(!mask || sigma > 0.0f, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: mask output requires sigma > 0");
   ACFM_REQUIRE(faces_batch_stride == 0 || faces_batch_stride == (int64_t)F * 3, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: faces_batch_stride must be 0 or F*3");
   if (N == 0) return ACFM_OK;
-  ACFM_REQUIRE(pix_to_face && zbuf && dists, ACFM_ERR_BAD_ARG, "acfm_raster_fwd: null output pointer");
+  ACFM_REQUIRE(lean || (pix_to_face && zbuf && dists), ACFM_ERR_BAD_ARG, "acfm_raster_fwd: null output pointer");
   ACFM_REQUIRE((ndc || V == 0) && (faces || F == 0), ACFM_ERR_BAD_ARG, "acfm_raster_fwd: null input pointer");
   ACFM_REQUIRE(F <= 65535 && V <= 65535, ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: V=%d, F=%d must be <= 65535", V, F);
   RasterParams p;
@@ -1510,6 +1540,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
   p.clip = clip_bary; p.cull = cull_backfaces;
   p.k_eps = acfm_raster_epsilon();
   p.loss_target = loss_target; p.loss_edt = loss_edt; p.NB = NB > 0 ? NB : 1; p.loss_part = nullptr;
+  p.lean_f = nullptr; p.lean_d = nullptr;
   p.p2f = (long long*)pix_to_face; p.zbuf = zbuf; p.dists = dists; p.bary = bary; p.mask = mask; p.vis = visible_verts;
   p.regions_x = (W + kRegion - 1) / kRegion; p.regions_y = (H + kRegion - 1) / kRegion;
   p.vec_ok = ((((uintptr_t)pix_to_face) | ((uintptr_t)zbuf) | ((uintptr_t)dists)) & 15u) == 0;
@@ -1525,6 +1556,16 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
   const long long ctas = (long long)N * p.regions_x * p.regions_y;
   ACFM_REQUIRE(ctas < (1ll << 28), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd: too many CTAs");
   cudaStream_t st = (cudaStream_t)stream;
+  if (lean) {
+    // lean mode: the K-nearest-set kernel only (the reference's K = 20), work lists required, fragments to the compact scratch
+    ACFM_REQUIRE(fwd_sets(K, nw), ACFM_ERR_UNSUPPORTED, "acfm_raster_fwd_lean: built for faces_per_pixel = 20 (got K=%d, V=%d, F=%d)", K, V, F);
+    ACFM_REQUIRE(workspace && mask && F < 65535, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_lean: needs the workspace, a mask output and F < 65535");
+    ACFM_REQUIRE(lean_bytes >= ctas * (long long)(kRegion * kRegion) * K * 6 && (((uintptr_t)lean_workspace) & 15u) == 0, ACFM_ERR_BAD_ARG,
+                 "acfm_raster_fwd_lean: lean workspace must be 16-byte aligned and hold acfm_raster_lean_workspace_bytes()");
+    p.lean_d = (float*)lean_workspace;                                                        // [U][1024][K] f32
+    p.lean_f = (unsigned short*)((float*)lean_workspace + ctas * (long long)(kRegion * kRegion) * K);   // [U][1024][K] u16
+    ACFM_CUDA_OK(cudaMemsetAsync(mask, 0, sizeof(float) * (size_t)N * H * W, st));         // regions and tiles without fragments
+  }
   if (visible_verts && V > 0) ACFM_CUDA_OK(cudaMemsetAsync(visible_verts, 0, sizeof(float) * (size_t)N * V, st));
   if (loss_sums) {
     // fused losses: region partials (zero where nothing is rendered) + per-target base sums, both in the caller's scratch
@@ -1557,7 +1598,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
     p.bulk_ok = p.vec_ok && (((long long)W * K) & 3) == 0 && (!bary || (((uintptr_t)bary) & 15u) == 0) && !tune.fill_lsu;
     // at most one wave, one CTA per SM: all of them are resident (and have signalled) before the rasterizer is dispatched
     const int fill_ctas = tune.fill_abs > 0 ? tune.fill_abs : (int)std::min<long long>(ctas, (long long)sms * tune.fill_per_sm);
-    if (tune.only != 'r') {
+    if (tune.only != 'r' && !lean) {
       raster_fill_kernel<<<fill_ctas, kFillThreads, fill_pattern_slots(K) * 12, st>>>(p, ws);
       ACFM_LAUNCH_OK("raster_fill_kernel");
       overlap = !tune.no_pdl;
@@ -1567,6 +1608,7 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
 #define ACFM_FWD_CASE(NW, KT)                                                                          \
   rc = faces_i64 ? launch_fwd<NW, long long, KT>(p, smem, (int)ctas, overlap, st) : launch_fwd<NW, int, KT>(p, smem, (int)ctas, overlap, st)
   if (workspace && tune.only == 'f') rc = ACFM_OK;
+  else if (lean) rc = faces_i64 ? launch_fwd<8, long long, 20, true>(p, smem, (int)ctas, false, st) : launch_fwd<8, int, 20, true>(p, smem, (int)ctas, false, st);
   else if (fwd_sets(K, nw)) ACFM_FWD_CASE(8, 20);  // the reference's faces_per_pixel: straight-line set operations
   else if (nw == 8 && K == 1) ACFM_FWD_CASE(8, 1);    // its hard renders (texture branch, OF_NeuralRenderer): z-buffer in registers
   else if (nw == 8) ACFM_FWD_CASE(8, 0);
@@ -1580,6 +1622,24 @@ int raster_fwd_impl(const float* ndc, const void* faces, int faces_i64, int64_t 
   return rc;
 }
 }  // namespace
+
+extern "C" int64_t acfm_raster_lean_workspace_bytes(int N, int H, int W, int K) {
+  if (N <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+  return (int64_t)N * ((W + kRegion - 1) / kRegion) * ((H + kRegion - 1) / kRegion) * (kRegion * kRegion) * K * 6;
+}
+
+extern "C" int acfm_raster_fwd_lean(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F,
+                                    int H, int W, int K, float blur_radius, float sigma, float* mask, float* visible_verts,
+                                    const float* target, const float* edt, int NB, float* loss_sums, void* loss_workspace,
+                                    int64_t loss_workspace_bytes, void* lean_workspace, int64_t lean_workspace_bytes, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  ACFM_REQUIRE(mask && lean_workspace && workspace, ACFM_ERR_BAD_ARG, "acfm_raster_fwd_lean: null mask / lean workspace / workspace pointer");
+  ACFM_REQUIRE(!loss_sums || (target && loss_workspace), ACFM_ERR_BAD_ARG, "acfm_raster_fwd_lean: loss_sums needs target and loss_workspace");
+  ACFM_REQUIRE(!loss_sums || (NB > 0 && N % NB == 0), ACFM_ERR_BAD_ARG, "acfm_raster_fwd_lean: N=%d is not a multiple of NB=%d", N, NB);
+  return raster_fwd_impl(ndc, faces, faces_i64, faces_batch_stride, N, V, F, H, W, K, blur_radius, 0, 0, sigma, nullptr, nullptr, nullptr,
+                         nullptr, mask, visible_verts, loss_sums ? target : nullptr, loss_sums ? edt : nullptr, NB, loss_sums,
+                         loss_workspace, loss_workspace_bytes, workspace, workspace_bytes, stream, lean_workspace, lean_workspace_bytes);
+}
 
 extern "C" int64_t acfm_raster_fwd_workspace_bytes(int N, int H, int W) {
   if (N <= 0 || H <= 0 || W <= 0) return 0;

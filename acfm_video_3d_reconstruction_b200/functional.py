@@ -266,3 +266,81 @@ def soft_silhouette_losses(ndc, faces, image_size, target, edt=None, blur_radius
     (loss_utils.losses_from_sums turns them into l1 / iou / edt losses)."""
     return _SoftSilhouetteLosses.apply(ndc, faces, target, edt, int(image_size), float(blur_radius), int(faces_per_pixel),
                                        float(sigma), bool(want_vis))
+
+
+# ---- lean training mode (not API parity; bench.py reports it separately) -----------------------------------------------------
+class _SoftSilhouetteLean(torch.autograd.Function):
+    """acfm_raster_fwd_lean / acfm_raster_soft_bwd_lean: mask, the fused loss sums and the visible-vertex map WITHOUT the (N,H,W,K)
+    fragment tensors — the fragments of the regions the mesh touches stay in a compact scratch between forward and backward."""
+
+    @staticmethod
+    def forward(ctx, ndc, faces, target, edt, image_size, blur_radius, K, sigma, want_vis):
+        _lib.require_cuda(ndc, faces, target, edt)
+        ndc = _f32c(ndc)
+        N, V, _ = ndc.shape
+        H = W = int(image_size)
+        fa, i64, fstride, F = _faces_arg(faces, N)
+        dev = ndc.device
+        NB = 0
+        if target is not None:
+            target = _f32c(target)
+            edt = _f32c(edt) if edt is not None else None
+            NB = target.shape[0]
+            if N and (NB == 0 or N % NB or target.numel() != NB * H * W or (edt is not None and edt.numel() != target.numel())):
+                raise ValueError(f"renders {N} vs target {tuple(target.shape)}: the batch must divide, the pixels must match")
+        L = _lib.lib()
+        mask = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+        sums = torch.empty((N, 4), dtype=torch.float32, device=dev) if target is not None else None
+        vis = torch.empty((N, V), dtype=torch.float32, device=dev) if want_vis else None
+        ws = torch.empty((max(int(L.acfm_raster_fwd_workspace_bytes(N, H, W)), 16),), dtype=torch.uint8, device=dev)
+        lean = torch.empty((max(int(L.acfm_raster_lean_workspace_bytes(N, H, W, K)), 16),), dtype=torch.uint8, device=dev)
+        lw_bytes = int(L.acfm_raster_loss_workspace_bytes(N, max(NB, 1), H, W)) if target is not None else 0
+        lw = torch.empty((max(lw_bytes, 16),), dtype=torch.uint8, device=dev) if target is not None else None
+        if N:
+            with torch.cuda.device(dev):
+                st = L.acfm_raster_fwd_lean(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, H, W, K, float(blur_radius), float(sigma),
+                                            _lib.ptr(mask), _lib.ptr(vis), _lib.ptr(target), _lib.ptr(edt), NB, _lib.ptr(sums), _lib.ptr(lw),
+                                            lw_bytes, _lib.ptr(lean), lean.numel(), _lib.ptr(ws), ws.numel(), _lib.stream_of(ndc))
+            _lib.check(st, "acfm_raster_fwd_lean")
+            _lib.count(3 + (2 if sums is not None else 0) + (1 if vis is not None else 0))   # mask memset, prep, rasterizer, ...
+        ctx.save_for_backward(ndc, faces, mask, target, edt)
+        ctx.cfg = (H, int(K), float(sigma))
+        ctx.scratch = (lean, ws)
+        ctx.set_materialize_grads(False)
+        outs = (mask,) + ((sums,) if sums is not None else ()) + ((vis,) if vis is not None else ())
+        if vis is not None:
+            ctx.mark_non_differentiable(vis)
+        ctx.has_sums = sums is not None
+        return outs if len(outs) > 1 else mask
+
+    @staticmethod
+    def backward(ctx, grad_mask, *rest):
+        ndc, faces, mask, target, edt = ctx.saved_tensors
+        grad_sums = rest[0] if (ctx.has_sums and rest) else None
+        none = (None,) * 9
+        N, V, _ = ndc.shape
+        if (grad_mask is None and grad_sums is None) or N == 0:
+            return none
+        S, K, sigma = ctx.cfg
+        lean, ws = ctx.scratch
+        fa, i64, fstride, F = _faces_arg(faces, N)
+        grad_mask = _f32c(grad_mask) if grad_mask is not None else None
+        grad_sums = _f32c(grad_sums) if grad_sums is not None else None
+        g = torch.empty_like(ndc)
+        with torch.cuda.device(ndc.device):
+            st = _lib.lib().acfm_raster_soft_bwd_lean(_lib.ptr(ndc), _lib.ptr(fa), i64, fstride, N, V, F, S, S, K, sigma, _lib.ptr(mask),
+                                                      _lib.ptr(grad_mask), _lib.ptr(grad_sums), _lib.ptr(target), _lib.ptr(edt),
+                                                      target.shape[0] if target is not None else 1, _lib.ptr(g), _lib.ptr(lean), _lib.ptr(ws),
+                                                      _lib.stream_of(ndc))
+        _lib.check(st, "acfm_raster_soft_bwd_lean")
+        _lib.count(2)
+        return (g,) + none[1:]
+
+
+def soft_silhouette_lean(ndc, faces, image_size, target=None, edt=None, blur_radius=BLUR_SOFT, faces_per_pixel=K_SOFT, sigma=SIGMA,
+                         want_vis=False):
+    """Lean training render: -> mask [, sums (N,4) if a target is given] [, vis].  No pix_to_face / zbuf / dists: use it where the
+    step consumes only the silhouette, its losses and the visible vertices (the reference's monocular step); same values and
+    gradients as soft_silhouette_losses.  K = 20 only."""
+    return _SoftSilhouetteLean.apply(ndc, faces, target, edt, int(image_size), float(blur_radius), int(faces_per_pixel), float(sigma),
+                                     bool(want_vis))

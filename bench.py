@@ -221,8 +221,13 @@ class HotPath:
         pred_v, ndc = deform.deform_and_project(self.mean_v, W, delta, cam_pred, offset_z=cfg["offset_z"])
         # the render with the mask-loss sums fused into its epilogue (NeuralRenderer.forward_with_losses); the full loss set
         # also takes the visible-vertex map from the render (the boundary loss below)
-        out = F_.soft_silhouette_losses(ndc, self.faces, cfg["img"], target, edt, F_.BLUR_SOFT, cfg["K"], F_.SIGMA, want_vis=full)
-        mask, p2f, sums = out[0], out[1], out[4]
+        if getattr(self, "lean", False) and not full:
+            # lean training mode (side measurement `lean`): no fragment tensors, compact fragments between forward and backward
+            mask, sums = F_.soft_silhouette_lean(ndc, self.faces, cfg["img"], target, edt, F_.BLUR_SOFT, cfg["K"], F_.SIGMA)
+            out, p2f = None, None
+        else:
+            out = F_.soft_silhouette_losses(ndc, self.faces, cfg["img"], target, edt, F_.BLUR_SOFT, cfg["K"], F_.SIGMA, want_vis=full)
+            mask, p2f, sums = out[0], out[1], out[4]
         per = loss_utils.combine_mask_losses(sums, cfg["img"] * cfg["img"], w_l1=1.0, w_edt=W_EDT)   # l1 + W_EDT * edt per render
         if full:
             G, NB, T = cfg["G"], cfg["frames"], cfg["clip_frames"]
@@ -463,6 +468,33 @@ def run_ours(args):
                 out["roofline_bwd"]["frac"] = out["roofline_bwd"]["achieved"] / peak
         except Exception:
             pass
+    def lean_bench():
+        """Side measurement (NOT the headline, not API parity): the same C2 step with the render in lean training mode —
+        mask + fused loss sums, no (N,H,W,K) fragment tensors, no padding kernel; the fragments of the live regions stay in a
+        compact scratch for the backward (SURVEY.md 8d / BASELINE.md section 3 "lean mode")."""
+        if cfg.get("full") or cfg["K"] != 20:
+            return {"skipped": "lean mode is built for the K = 20 mask step"}
+        hp.lean = True
+        try:
+            ref_loss = float(hp.step(*dev_in, world=1)[0])
+            for _ in range(3):
+                hp.step(*dev_in, world=1)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                hp.step(*dev_in, world=1)
+            b.record()
+            torch.cuda.synchronize()
+            ms_l = a.elapsed_time(b) / args.steps
+        finally:
+            hp.lean = False
+        par_loss = float(hp.step(*dev_in, world=1)[0])
+        return {"value": N_r / (ms_l * 1e-3), "unit": "renders/s (this GPU)", "ms_per_step": ms_l,
+                "loss_equals_parity_mode": bool(ref_loss == par_loss),
+                "note": "lean training mode: silhouette, loss sums and gradients identical to the API-parity step, but pix_to_face / zbuf / "
+                        "dists are not materialised (no padding is written); reported separately, never in `value`"}
+
     def side(key, fn):
         # side measurements must never cost the headline line: a failure is reported in place of the number
         try:
@@ -470,6 +502,7 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    side("lean", lean_bench)
     if world == 1:
         side("target_maps", lambda: target_maps_bench(hp, cfg, peak, cpu=not args.no_cpu_baseline))
         side("post_optimize", lambda: post_optimize_bench(hp, cfg, cpu=not args.no_cpu_baseline))

@@ -156,6 +156,23 @@ int acfm_raster_soft_bwd_train(const float* ndc, const void* faces, int faces_i6
                                const float* target, const float* edt, int NB, float* grad_ndc, const void* fwd_workspace,
                                void* stream);
 
+/* LEAN training mode (not API-parity: reported separately by bench.py).  The same render for a caller that needs the silhouette,
+ * the loss sums and the visible-vertex map but NOT the (N,H,W,K) fragment tensors (87 % of whose bytes are -1 padding at the
+ * reference's workloads): the fragments of the regions the mesh touches go, compact (2 + 4 bytes each: face id within the render,
+ * signed distance), to lean_workspace (acfm_raster_lean_workspace_bytes(), 16-byte aligned) for acfm_raster_soft_bwd_lean; no
+ * padding is written anywhere.  mask, loss_sums, visible_verts: bit-identical to acfm_raster_fwd_train's; gradient: the same
+ * arithmetic on the same fragments.  Needs the workspace (work lists); built for K = 20 (the reference's faces_per_pixel) on
+ * 8-warp CTAs, ACFM_ERR_UNSUPPORTED otherwise; F < 65535. */
+int64_t acfm_raster_lean_workspace_bytes(int N, int H, int W, int K);
+int acfm_raster_fwd_lean(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F, int H,
+                         int W, int K, float blur_radius, float sigma, float* mask, float* visible_verts, const float* target,
+                         const float* edt, int NB, float* loss_sums, void* loss_workspace, int64_t loss_workspace_bytes,
+                         void* lean_workspace, int64_t lean_workspace_bytes, void* workspace, int64_t workspace_bytes, void* stream);
+int acfm_raster_soft_bwd_lean(const float* ndc, const void* faces, int faces_i64, int64_t faces_batch_stride, int N, int V, int F,
+                              int H, int W, int K, float sigma, const float* mask, const float* grad_mask, const float* grad_sums,
+                              const float* target, const float* edt, int NB, float* grad_ndc, const void* lean_workspace,
+                              const void* fwd_workspace, void* stream);
+
 /* Backward of rasterize_meshes + sigmoid_alpha_blend for the silhouette
  * (_C.rasterize_meshes_backward with grad only on dists).
  * grad_mask (N,H,W); grad_ndc (N,V,3) is overwritten (z component = 0).

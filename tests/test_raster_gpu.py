@@ -637,3 +637,45 @@ def test_hard_render_depth_culls_are_exact(clip, blur):
     assert np.array_equal(out["bary"].cpu().numpy(), ref["bary"])
     hit = ref["pix_to_face"][..., 0] % F
     assert (ref["pix_to_face"] >= 0).mean() > 0.5 and ((hit >= nbig) & (ref["pix_to_face"][..., 0] >= 0)).sum() > 50   # tiny faces do win pixels
+
+
+@pytest.mark.parametrize("with_target", [True, False])
+def test_lean_mode_equals_the_parity_route(with_target):
+    """acfm_raster_fwd_lean / _soft_bwd_lean (no fragment tensors; compact fragments of the live regions between forward and
+    backward): silhouette, fused loss sums and visible vertices bit-identical to the API-parity render's, same gradient."""
+    from acfm_video_3d_reconstruction_b200 import functional as F_
+    from acfm_video_3d_reconstruction_b200 import NeuralRenderer
+    v, f = util.template("bird")
+    N, S, NB = 6, 160, 3
+    X, cam = util.synth_verts(v, N, seed=71), util.synth_cams(N, seed=72)
+    cam[1, 1] += 1.2                                          # one render mostly off screen
+    ndc = NeuralRenderer(S, offset_z=5.0).to_ndc(torch.from_numpy(X).cuda(), torch.from_numpy(cam).cuda()).detach()
+    faces = torch.from_numpy(f).cuda()[None]
+    gen = torch.Generator().manual_seed(9)
+    target = (torch.rand(NB, S, S, generator=gen) > 0.6).float().cuda() if with_target else None
+    edt = torch.rand(NB, S, S, generator=gen).cuda() if with_target else None
+    gm = torch.randn(N, S, S, generator=gen).cuda()
+    gs = (torch.randn(N, 4, generator=gen) * 1e-3).cuda()
+
+    def run(lean):
+        x = ndc.clone().requires_grad_(True)
+        if lean:
+            out = F_.soft_silhouette_lean(x, faces, S, target, edt, want_vis=True)
+            mask, sums, vis = (out[0], out[1], out[2]) if with_target else (out[0], None, out[1])
+        elif with_target:
+            mask, _, _, _, sums, vis = F_.soft_silhouette_losses(x, faces, S, target, edt, want_vis=True)
+        else:
+            mask, _, _, _, vis = F_.soft_silhouette(x, faces, S, want_vis=True)
+            sums = None
+        loss = (mask * gm).sum() + ((sums * gs).sum() if sums is not None else 0.0)
+        g, = torch.autograd.grad(loss, x)
+        return mask.detach(), sums, vis, g
+
+    m0, s0, v0, g0 = run(False)
+    m1, s1, v1, g1 = run(True)
+    assert torch.equal(m0, m1) and torch.equal(v0, v1) and float(m0.sum()) > 100
+    if with_target:
+        assert torch.equal(s0, s1)
+    assert util.rel_err(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-4 and float(g0.abs().sum()) > 0
+    with pytest.raises(ValueError):                          # built for the reference's K = 20 only (unsupported size)
+        F_.soft_silhouette_lean(ndc, faces, S, faces_per_pixel=8)
