@@ -38,8 +38,11 @@
 //          unsorted, append or replace-the-farthest, no shifting; other K: round 1's sorted list) in shared memory;
 //      (d) one rank pass puts every lane's set in depth order (K = 20), the silhouette is blended in that order, the fused
 //          mask-loss sums are accumulated, and pix_to_face / zbuf / dists are written with 16-byte stores.
-//   Region faces beyond `cap` (meshes that are tiny on screen) go through a slower face-uniform path
+//   Region faces beyond `cap` (regions that see more than 256 faces) go through a face-uniform path
 //   with on-the-fly set-up broadcast by warp shuffles.
+//   Template variants: KT = 20 the K-nearest sets, KT = 1 the hard renders (nearest fragment in registers, faces behind it
+//   dropped at the filter / scan stage), KT = 0 every other K (sorted lists); LEAN (acfm_raster_fwd_lean): step (d) writes
+//   compact fragments of the covered pixels to a scratch for the backward instead of the padded (N,H,W,K) tensors.
 //
 // Conservative edge equations.  For edge i (opposite vertex i) with numerator n_i(p) (w_i = n_i/den),
 // a pixel with sign(den)*n_i(p) < 0 lies outside that edge's line, at distance |n_i|/|e_i| from it and
