@@ -105,7 +105,14 @@ def _hot_path(wl, S, K, dev):
     total = (per["l1"] + 0.5 * per["iou_loss"] + 0.1 * per["edt"]).sum() + (out[0] * out[0]).mean()
     total.backward()
     hard = F_.rasterize(ndc.detach(), faces, S, 0.0, 1, want_bary=True)
-    return dict(mask=out[0], p2f=out[1], zbuf=out[2], dists=out[3], sums=out[4], vis=out[5], edt=edt, bds=bds,
+    lean_mask, lean_g = out[0], delta.grad
+    if K == 20:   # the lean training render (compact fragment scratch between forward and backward)
+        x = ndc.detach().clone().requires_grad_(True)
+        lm, ls, lv = F_.soft_silhouette_lean(x, faces, S, target, edt, want_vis=True)
+        lean_g, = torch.autograd.grad((lm * lm).mean() + ls.sum() * 1e-4, x)
+        lean_mask = lm.detach()
+        assert torch.equal(lean_mask, out[0].detach()) and torch.equal(ls, out[4]) and torch.equal(lv, out[5])
+    return dict(lean_mask=lean_mask, lean_g=lean_g, mask=out[0], p2f=out[1], zbuf=out[2], dists=out[3], sums=out[4], vis=out[5], edt=edt, bds=bds,
                 hard_p2f=hard["pix_to_face"], hard_bary=hard["bary"], W=W.detach(),
                 g_delta=delta.grad, g_cams=cams.grad, g_lbs=lbs_param.grad)
 
@@ -120,9 +127,9 @@ def test_no_write_outside_any_buffer(S, K, frames, G):
         got = _hot_path(wl, S, K, dev)
         n = ga.check()
     assert n >= 20, n                                        # the patched allocators were the ones in use
-    for k in ("mask", "p2f", "zbuf", "dists", "sums", "vis", "edt", "bds", "hard_p2f", "hard_bary", "W"):
+    for k in ("mask", "p2f", "zbuf", "dists", "sums", "vis", "edt", "bds", "hard_p2f", "hard_bary", "W", "lean_mask"):
         assert torch.equal(got[k], want[k]), k               # forward: deterministic, bit for bit
-    for k in ("g_delta", "g_cams", "g_lbs"):                 # backward: float atomics, order differs between runs
+    for k in ("g_delta", "g_cams", "g_lbs", "lean_g"):       # backward: float atomics, order differs between runs
         assert util.rel_err(got[k].cpu().numpy(), want[k].cpu().numpy()) < 1e-4, k
 
 
