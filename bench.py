@@ -64,6 +64,63 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------------------
 # clocks sampler
 # ---------------------------------------------------------------------------------------------------------------
+class ClocksNvml:
+    """SM clock and clock-event reasons sampled through NVML every ~4 ms from a thread (nvidia-smi's fastest loop, 50 ms, puts
+    one or two samples into a 65 ms timed region); same result keys as Clocks below, which is the fallback."""
+
+    def __init__(self, index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        uuid = None
+        try:   # honour CUDA_VISIBLE_DEVICES: NVML enumerates every GPU of the box
+            uuid = torch.cuda.get_device_properties(index).uuid
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)   # fail here, not in the thread
+        self.rows, self.stop_flag = [], False
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), float(sm), int(r)))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self, t0, t1):
+        nv = self.nv
+        self.stop_flag = True
+        self.th.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        window = "timed"
+        if len(rows) < 3:
+            rows, window = self.rows, "warmup+timed"
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        reasons = sorted({n for _, _, r in rows for n, bit in names if r & bit})
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons, "samples": len(sm),
+                "window": window, "source": "nvml, 4 ms"}
+
+
+def make_clocks(index):
+    try:
+        return ClocksNvml(index)
+    except Exception:
+        return Clocks(index)
+
+
 class Clocks:
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -290,7 +347,7 @@ def run_ours(args):
 
     dev_in = hp.h2d()
     torch.cuda.synchronize()
-    clocks = Clocks(local) if rank == 0 else None
+    clocks = make_clocks(local) if rank == 0 else None
     for _ in range(args.warmup):
         hp.step(*dev_in, world=world)
     kev.clear()
